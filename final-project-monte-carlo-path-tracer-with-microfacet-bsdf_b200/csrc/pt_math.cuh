@@ -1,0 +1,721 @@
+// csrc/pt_math.cuh — per-ray / per-vertex arithmetic of the wavefront tracer (device functions).
+//
+// Every function names the reference code whose arithmetic it reproduces.  The reference does
+// its vector algebra through Eigen's fixed-size Vector3f; the operation order used here is the
+// one those expressions evaluate to (size-3 reductions associate as a0 + (a1 + a2),
+// normalized() divides by sqrt(squaredNorm), scalar operands are converted to float first).
+// The translation unit is compiled with -fmad=false and IEEE division / square root so that
+// ray geometry (hits, t, sampled directions, light points) is bit-identical to the CPU code:
+// every branch a path takes depends on geometry only, hence paths follow the same vertices.
+//
+// The functions are declared __host__ __device__ so that tests/hostcheck can compile this
+// header with g++ and check it against the oracle on a machine without a GPU; the shipped
+// library only contains the device instantiation (there is no CPU render path).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PT_HD __host__ __device__ __forceinline__
+#else
+#define PT_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define PT_LDG4(p) __ldg(reinterpret_cast<const float4 *>(p))
+#define PT_LDG(p) __ldg(p)
+#else
+#define PT_LDG4(p) (*reinterpret_cast<const float4 *>(p))
+#define PT_LDG(p) (*(p))
+#endif
+
+namespace pt {
+
+constexpr float kEps = 1e-4f;                  // EPSILON, src/Renderer.cpp:15
+constexpr float kPi = 3.141592653589793f;      // M_PI redefined as float, src/global.hpp:8-9
+constexpr int kStackSize = 40;
+
+enum { MAT_SMOOTH_CONDUCTOR = 0, MAT_ROUGH_CONDUCTOR = 1, MAT_SMOOTH_DIELECTRIC = 2, MAT_ROUGH_DIELECTRIC = 3 };
+enum { NODE_INTERIOR = 0, NODE_TRIANGLE = 1, NODE_SPHERE = 2, NODE_EMPTY = 3 };
+
+// ---- Vector3f ------------------------------------------------------------------------------
+struct f3 { float x, y, z; };
+PT_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+PT_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PT_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PT_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+PT_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+PT_HD f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+PT_HD f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+PT_HD float dot(f3 a, f3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+PT_HD float sqnorm(f3 a) { return dot(a, a); }
+PT_HD float norm(f3 a) { return sqrtf(sqnorm(a)); }
+PT_HD f3 normalized(f3 a) {
+    float n2 = sqnorm(a);
+    return (n2 > 0.f) ? a / sqrtf(n2) : a;
+}
+PT_HD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+PT_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c;
+    c.f = f;
+    return c.u;
+#endif
+}
+PT_HD f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+PT_HD float comp(f3 v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
+
+// clamp(lo, hi, v) = std::max(lo, std::min(hi, v)), src/global.hpp:16-18 (NaN -> hi).
+PT_HD float clamp_ref(float lo, float hi, float v) {
+    float m = (v < hi) ? v : hi;
+    return (lo < m) ? m : lo;
+}
+
+// ---- sample streams (replace std::mt19937 + random_device, src/global.hpp:42-53) ---------------
+// Philox4x32-10; stream (pixel, sample, tag); draw `dim` = word dim&3 of block dim>>2.
+PT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+enum { STREAM_PATH = 0, STREAM_CAMERA = 1 };
+struct Stream {
+    uint32_t k0, k1, pixel, sample, tag, dim;
+    uint32_t blk, w[4];
+};
+PT_HD Stream stream_open(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t tag, uint32_t dim) {
+    Stream s;
+    s.k0 = k0; s.k1 = k1; s.pixel = pixel; s.sample = sample; s.tag = tag; s.dim = dim;
+    s.blk = 0xFFFFFFFFu;
+    s.w[0] = s.w[1] = s.w[2] = s.w[3] = 0;
+    return s;
+}
+// uniform_real_distribution<float>(0,1) on a 32-bit engine word whose low 8 bits are clear:
+// exactly (word >> 8) * 2^-24.
+PT_HD float stream_next(Stream &s) {
+    uint32_t b = s.dim >> 2;
+    if (b != s.blk) {
+        philox4x32_10(s.pixel, s.sample, b, s.tag, s.k0, s.k1, s.w);
+        s.blk = b;
+    }
+    uint32_t i = s.dim & 3u;
+    uint32_t word = (i == 0) ? s.w[0] : (i == 1) ? s.w[1] : (i == 2) ? s.w[2] : s.w[3];
+    s.dim++;
+    return (float)(word >> 8) * 5.9604644775390625e-08f;
+}
+
+// ---- sin / cos --------------------------------------------------------------------------------
+// The two places where the reference feeds sin/cos back into ray geometry (Renderer.cpp:58-60,
+// Material.hpp:114-119) are evaluated in IEEE double with a fixed operation order (Cody-Waite
+// reduction by pi/2, fdlibm kernel polynomials), so host and device agree bit for bit.
+PT_HD void sincos_portable(float xf, float *s_out, float *c_out) {
+    const double x = (double)xf;
+    const double two_over_pi = 6.36619772367581382433e-01;
+    const double pio2_hi = 1.57079632673412561417e+00;
+    const double pio2_lo = 6.07710050650619224932e-11;
+    double t = x * two_over_pi;
+    double kd = (t >= 0.0) ? (double)(long long)(t + 0.5) : -(double)(long long)(0.5 - t);
+    long long k = (long long)kd;
+    double r = (x - kd * pio2_hi) - kd * pio2_lo;
+    double z = r * r;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double ps = S6;
+    ps = ps * z + S5; ps = ps * z + S4; ps = ps * z + S3; ps = ps * z + S2; ps = ps * z + S1;
+    double sr = r + (r * z) * ps;
+    double pc = C6;
+    pc = pc * z + C5; pc = pc * z + C4; pc = pc * z + C3; pc = pc * z + C2; pc = pc * z + C1;
+    double cr = (1.0 - 0.5 * z) + (z * z) * pc;
+    double sd, cd;
+    switch ((int)(k & 3)) {
+    case 0: sd = sr; cd = cr; break;
+    case 1: sd = cr; cd = -sr; break;
+    case 2: sd = -sr; cd = -cr; break;
+    default: sd = -cr; cd = sr; break;
+    }
+    *s_out = (float)sd;
+    *c_out = (float)cd;
+}
+
+// ---- scene view ----------------------------------------------------------------------------------
+struct Material {
+    int type;
+    float emission[3];
+    float ior_a, ior_b, roughness;
+    float refl[3];
+    int textured;
+    int emissive;  // Material::hasEmission(), src/Material.hpp:263
+};
+struct SceneView {
+    const float4 *nodes;    // 2 float4 per node: (bmin, a) (bmax, kind)
+    const float4 *v0, *e1, *e2, *nrm;  // per primitive
+    const float *v1v2, *uv;            // 6 floats per primitive
+    const uint32_t *prim_mat, *prim_kind;
+    const Material *mats;
+    int n_lights;
+    const float *light_area;
+    const uint32_t *light_root, *light_mat;
+    const float *ln_area;
+    const int *ln_left, *ln_right, *ln_prim;
+    int use_env, env_w, env_h;
+    const float4 *env;      // texels as float4 (rgb, 0)
+    float bg[3];
+    float rr_rate, inv_rr;
+    int enable_shadow, n_dir;
+};
+
+// ---- Ray, src/Ray.hpp:6-29 -------------------------------------------------------------------------
+struct Ray {
+    f3 o, d, inv;
+};
+PT_HD Ray make_ray(f3 o, f3 d) {
+    Ray r;
+    r.o = o; r.d = d;
+    // direction_inv = Vector3f(1./x, 1./y, 1./z): a double quotient narrowed to float, which equals
+    // the correctly rounded float quotient (53 >= 2*24+2 bits: the double rounding is innocuous).
+    r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    return r;
+}
+
+// ---- Bounds3::IntersectP, src/Bounds3.hpp:95-108 ------------------------------------------------------
+PT_HD bool box_hit(f3 pmin, f3 pmax, const Ray &r, float *tmin_out) {
+    float t1x = (pmin.x - r.o.x) * r.inv.x, t1y = (pmin.y - r.o.y) * r.inv.y, t1z = (pmin.z - r.o.z) * r.inv.z;
+    float t2x = (pmax.x - r.o.x) * r.inv.x, t2y = (pmax.y - r.o.y) * r.inv.y, t2z = (pmax.z - r.o.z) * r.inv.z;
+    float mnx = fminf(t1x, t2x), mny = fminf(t1y, t2y), mnz = fminf(t1z, t2z);
+    float mxx = fmaxf(t1x, t2x), mxy = fmaxf(t1y, t2y), mxz = fmaxf(t1z, t2z);
+    // std::max({a,b,c}) / std::min({a,b,c}): sequential `<` comparisons (NaN keeps the running value)
+    float tmin = mnx;
+    if (tmin < mny) tmin = mny;
+    if (tmin < mnz) tmin = mnz;
+    float tmax = mxx;
+    if (mxy < tmax) tmax = mxy;
+    if (mxz < tmax) tmax = mxz;
+    *tmin_out = tmin;
+    return (tmin - kEps <= tmax) && (tmax >= -kEps);
+}
+
+// ---- Triangle::getIntersection, src/Triangle.hpp:222-252 ---------------------------------------------
+// float cross / dot products, then det_inv, u, v, t in double.
+PT_HD bool tri_hit(f3 v0, f3 e1, f3 e2, const Ray &r, double *t_out, double *u_out, double *v_out) {
+    f3 pvec = cross(r.d, e2);
+    double det = (double)dot(e1, pvec);
+    if (fabs(det) < (double)kEps) return false;
+    double det_inv = 1. / det;
+    f3 tvec = r.o - v0;
+    double u = (double)dot(tvec, pvec) * det_inv;
+    if (u < 0 || u > 1) return false;
+    f3 qvec = cross(tvec, e1);
+    double v = (double)dot(r.d, qvec) * det_inv;
+    if (v < 0 || u + v > 1) return false;
+    double t = (double)dot(e2, qvec) * det_inv;
+    if (t < 0) return false;
+    *t_out = t; *u_out = u; *v_out = v;
+    return true;
+}
+
+// ---- Sphere::getIntersection + solveQuadratic, src/Sphere.hpp:26-48, src/global.hpp:20-35 ------------
+PT_HD bool sphere_hit(f3 center, float radius2, const Ray &r, float *t_out) {
+    f3 L = r.o - center;
+    float a = dot(r.d, r.d);
+    float b = 2 * dot(r.d, L);
+    float c = dot(L, L) - radius2;
+    float discr = b * b - 4 * a * c;
+    float x0, x1;
+    if (discr < 0) return false;
+    else if (discr == 0) x0 = x1 = (float)(-0.5 * (double)b / (double)a);
+    else {
+        // unqualified sqrt() on a float: the C double sqrt
+        double sq = sqrt((double)discr);
+        float q = (b > 0) ? (float)(-0.5 * ((double)b + sq)) : (float)(-0.5 * ((double)b - sq));
+        x0 = q / a;
+        x1 = c / q;
+    }
+    if (x0 > x1) { float tmp = x0; x0 = x1; x1 = tmp; }
+    float t0 = x0;
+    if (t0 < 0) t0 = x1;
+    if (t0 < 0) return false;
+    *t_out = t0;
+    return true;
+}
+
+// ---- closest hit: Scene::intersect -> BVHAccel::getIntersection, src/Scene.cpp:19-21, src/BVH.cpp:95-116 --
+// The reference visits every node whose box test passes and keeps the smaller `double distance`,
+// ties going to the depth-first-later leaf.  Here: children are visited near-first and a subtree is
+// skipped when its box entry lies beyond the best hit by more than a conservative margin; the box
+// test itself is the reference's, so the set of candidate leaves with t <= best is the same.
+// Primitive ids are depth-first leaf numbers, so "later leaf wins" is "larger id wins".
+struct Hit {
+    double t;
+    int prim;  // -1 = miss
+};
+struct TravStats {
+    unsigned nodes, prims;
+};
+
+PT_HD float prune_bound(double best) {
+    float b = (float)best;
+    return b + (2e-3f + 1e-5f * b);
+}
+
+// primitive test of a leaf: Triangle::getIntersection or Sphere::getIntersection
+PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
+    float4 a = PT_LDG4(S.v0 + prim);
+    float4 b = PT_LDG4(S.e1 + prim);
+    if (kind == NODE_TRIANGLE) {
+        float4 c = PT_LDG4(S.e2 + prim);
+        double u, v;
+        return tri_hit(xyz(a), xyz(b), xyz(c), r, t, &u, &v);
+    }
+    float tf;
+    bool ok = sphere_hit(xyz(a), b.x, r, &tf);
+    *t = (double)tf;
+    return ok;
+}
+
+// nodes[0] is the root and nodes[1] an EMPTY filler, so the walk starts at sibling pair 0.
+template <bool COUNT>
+PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
+    Hit h;
+    h.t = 1.7976931348623157e308;  // Intersection::distance of a miss, src/Intersection.hpp:17
+    h.prim = -1;
+    float bound = INFINITY;
+    uint32_t stk[kStackSize];
+    float stk_t[kStackSize];
+    int sp = 0;
+    uint32_t pair = 0;
+    for (;;) {
+        const float4 *p = S.nodes + 4 * (size_t)pair;
+        float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
+        if (COUNT) st->nodes += 2;
+        uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
+        float tl = 0.f, tr = 0.f;
+        bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > bound);
+        bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > bound);
+        if (hl && lk != NODE_INTERIOR) {
+            double t;
+            if (COUNT) st->prims++;
+            if (prim_hit(S, la, lk, r, &t) && (t < h.t || (t == h.t && (int)la > h.prim))) {
+                h.t = t; h.prim = (int)la; bound = prune_bound(t);
+            }
+            hl = false;
+        }
+        if (hr && rk != NODE_INTERIOR) {
+            if (!(tr > bound)) {
+                double t;
+                if (COUNT) st->prims++;
+                if (prim_hit(S, ra, rk, r, &t) && (t < h.t || (t == h.t && (int)ra > h.prim))) {
+                    h.t = t; h.prim = (int)ra; bound = prune_bound(t);
+                }
+            }
+            hr = false;
+        }
+        if (hl && tl > bound) hl = false;
+        if (hr && tr > bound) hr = false;
+        if (hl && hr) {
+            bool left_near = !(tr < tl);
+            stk[sp] = left_near ? ra : la;
+            stk_t[sp] = left_near ? tr : tl;
+            sp++;
+            pair = left_near ? la : ra;
+            continue;
+        }
+        if (hl) { pair = la; continue; }
+        if (hr) { pair = ra; continue; }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (!(stk_t[sp] > bound)) { pair = stk[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+    return h;
+}
+
+// ---- visibility of a light sample: Scene::directLighting, src/Scene.cpp:72-75 -----------------------------
+// visible <=> the CLOSEST hit exists and |distance - dist| < EPSILON (compared in double).  Equivalent
+// without finding the closest hit: no hit with t <= dist - EPSILON exists (early exit when one is
+// found) and some hit lies inside the window; subtrees entered beyond the window are skipped.
+template <bool COUNT>
+PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st) {
+    const double eps = (double)kEps, dd = (double)dist;
+    const float bound = dist + (4e-3f + 1e-5f * dist);
+    bool in_window = false;
+    uint32_t stk[kStackSize];
+    int sp = 0;
+    uint32_t pair = 0;
+    for (;;) {
+        const float4 *p = S.nodes + 4 * (size_t)pair;
+        float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
+        if (COUNT) st->nodes += 2;
+        uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
+        float tl = 0.f, tr = 0.f;
+        bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > bound);
+        bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > bound);
+        if (hl && lk != NODE_INTERIOR) {
+            double t;
+            if (COUNT) st->prims++;
+            if (prim_hit(S, la, lk, r, &t)) {
+                if (fabs(t - dd) < eps) in_window = true;
+                else if (t < dd) return false;  // a closer hit outside the window: the closest hit fails the test
+            }
+            hl = false;
+        }
+        if (hr && rk != NODE_INTERIOR) {
+            double t;
+            if (COUNT) st->prims++;
+            if (prim_hit(S, ra, rk, r, &t)) {
+                if (fabs(t - dd) < eps) in_window = true;
+                else if (t < dd) return false;
+            }
+            hr = false;
+        }
+        if (hl && hr) {
+            bool left_near = !(tr < tl);
+            stk[sp++] = left_near ? ra : la;
+            pair = left_near ? la : ra;
+            continue;
+        }
+        if (hl) { pair = la; continue; }
+        if (hr) { pair = ra; continue; }
+        if (sp == 0) break;
+        pair = stk[--sp];
+    }
+    return in_window;
+}
+
+// ---- surface point of a hit: the Intersection the reference returns ---------------------------------------
+struct Surface {
+    f3 p, n;
+    float u, v;  // tcoords
+    uint32_t mat;
+};
+PT_HD Surface surface_at(const SceneView &S, const Ray &r, const Hit &h) {
+    Surface s;
+    uint32_t prim = (uint32_t)h.prim;
+    s.mat = PT_LDG(S.prim_mat + prim);
+    uint32_t kind = PT_LDG(S.prim_kind + prim);
+    s.p = r.o + r.d * (float)h.t;  // Ray::operator()(double t): the scalar is converted to float first
+    s.u = 0.f; s.v = 0.f;
+    if (kind == NODE_TRIANGLE) {
+        s.n = xyz(PT_LDG4(S.nrm + prim));
+        if (S.mats[s.mat].textured) {
+            // tcoords = (1 - u - v) * t0 + u * t1 + v * t2 with double u, v (Triangle.hpp:248)
+            double t, u, v;
+            tri_hit(xyz(PT_LDG4(S.v0 + prim)), xyz(PT_LDG4(S.e1 + prim)), xyz(PT_LDG4(S.e2 + prim)), r, &t, &u, &v);
+            const float *q = S.uv + 6 * (size_t)prim;
+            float w0 = (float)(1 - u - v), w1 = (float)u, w2 = (float)v;
+            s.u = (w0 * q[0] + w1 * q[2]) + w2 * q[4];
+            s.v = (w0 * q[1] + w1 * q[3]) + w2 * q[5];
+        }
+    } else {
+        float4 c = PT_LDG4(S.v0 + prim);
+        s.n = normalized(s.p - xyz(c));  // Sphere.hpp:42
+    }
+    return s;
+}
+
+// ---- Material, src/Material.hpp ---------------------------------------------------------------------------
+PT_HD float wavelength_um(int c) { return c == 0 ? 0.700f : (c == 1 ? 0.5461f : 0.4358f); }  // WaveLen.hpp:7-18
+PT_HD float mat_ior(const Material &m, int c) {  // getIor, Material.hpp:178-183
+    float wl = wavelength_um(c);
+    return m.ior_a + m.ior_b / (wl * wl);
+}
+PT_HD bool mat_is_conductor(const Material &m) { return m.type == MAT_SMOOTH_CONDUCTOR || m.type == MAT_ROUGH_CONDUCTOR; }
+PT_HD bool mat_is_rough(const Material &m) { return m.type == MAT_ROUGH_CONDUCTOR || m.type == MAT_ROUGH_DIELECTRIC; }
+PT_HD bool mat_is_dirac(const Material &m) { return !mat_is_rough(m); }
+
+PT_HD float mat_reflectance(const Material &m, float u, float v, int c) {  // getReflectance, :134-151
+    if (!m.textured) return m.refl[c];
+    int col = (int)((u - 0.05f) * 10);
+    int row = (int)((v - 0.00f) * 12);
+    if (col >= 3 && col <= 5 && row <= 7) {
+        bool white = (col + row) % 2 == 1;
+        return white ? 0.9f : 0.1f;
+    }
+    return 0.1f;
+}
+PT_HD float fresnel_schlick(const Material &m, float cos_theta, float u, float v, int c) {  // :80-86
+    float f = mat_reflectance(m, u, v, c);
+    float invc = 1.f - cos_theta;
+    float c2 = invc * invc;
+    return f + (1.f - f) * c2 * c2 * invc;
+}
+PT_HD float mat_fresnel(const Material &m, f3 I, f3 N, int c) {  // fresnel, :198-226
+    if (mat_is_conductor(m)) return 1;
+    float cosi = clamp_ref(-1, 1, dot(I, N));
+    float etai = 1, etat = mat_ior(m, c);
+    if (cosi > 0) { float t = etai; etai = etat; etat = t; }
+    float sint = etai / etat * sqrtf(fmaxf(0.f, 1 - cosi * cosi));
+    if (sint >= 1) return 1;
+    float cost = sqrtf(fmaxf(0.f, 1 - sint * sint));
+    cosi = fabsf(cosi);
+    float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+    float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+    return (Rs * Rs + Rp * Rp) / 2;
+}
+PT_HD f3 mat_refract(const Material &m, f3 I, f3 N, int c) {  // refract, :227-242
+    float cosi = clamp_ref(-1, 1, dot(I, N));
+    float etai = 1, etat = mat_ior(m, c);
+    f3 n = N;
+    if (cosi < 0) cosi = -cosi;
+    else { float t = etai; etai = etat; etat = t; n = -N; }
+    float eta = etai / etat;
+    float k = 1 - eta * eta * (1 - cosi * cosi);
+    if (k < 0) return mk3(0, 0, 0);
+    return eta * I + (eta * cosi - sqrtf(k)) * n;
+}
+PT_HD f3 mat_reflect(f3 I, f3 N) { return (2 * dot(N, I)) * N - I; }  // reflect, :195-197
+
+PT_HD float d_ggx(f3 h, f3 n, float alpha) {  // D_GGX, :26-34 — (alpha + tan^2), as written
+    float NoH = fabsf(dot(n, h));
+    if (NoH <= kEps && NoH >= -kEps) return 0.0f;
+    float tanTheta = sqrtf(1.0f - NoH * NoH) / NoH;
+    float alpha2 = alpha * alpha;
+    float denom = (NoH * NoH) * (alpha + tanTheta * tanTheta);
+    return alpha2 / (kPi * denom * denom);
+}
+PT_HD float g1_ggx(f3 v, f3 n, float alpha) {  // G1_SmithGGX, :38-69
+    float NoV = fabsf(dot(n, v));
+    if (NoV <= kEps && NoV >= -kEps) return 0.0f;
+    float tanTheta = sqrtf(1.0f - NoV * NoV) / NoV;
+    if (tanTheta == 0.0f) return 1.0f;
+    float al_tan = alpha * tanTheta;
+    return (float)(2. / (1. + (double)sqrtf(1 + al_tan * al_tan)));
+}
+PT_HD float g_ggx(f3 wi, f3 wo, f3 n, float alpha) { return g1_ggx(wi, n, alpha) * g1_ggx(wo, n, alpha); }
+
+// tanToWorld + ImportanceSampleGGX, :95-130.  xi_x / xi_y are Vector2f Xi's components.
+PT_HD f3 ggx_sample(float xi_x, float xi_y, float alpha, f3 n) {
+    float phi = 2.0f * kPi * xi_x;
+    float cosTheta = sqrtf((1.0f - xi_y) / (1.0f + (alpha * alpha - 1.0f) * xi_y));
+    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    float sp, cp;
+    sincos_portable(phi, &sp, &cp);
+    f3 tc = mk3(sinTheta * cp, sinTheta * sp, cosTheta);
+    f3 T;
+    if (fabsf(n.x) > fabsf(n.y)) {
+        float invLen = 1.0f / sqrtf(n.x * n.x + n.z * n.z);
+        T = mk3(-n.z * invLen, 0.0f, n.x * invLen);
+    } else {
+        float invLen = 1.0f / sqrtf(n.y * n.y + n.z * n.z);
+        T = mk3(0.0f, n.z * invLen, -n.y * invLen);
+    }
+    f3 B = cross(n, T);
+    return normalized((tc.x * T + tc.y * B) + tc.z * n);
+}
+
+// Material::sample -> sampleGGXMicrofacetNormal: `Vector2f Xi(get_random_float(), get_random_float())`.
+// The two calls are unsequenced function arguments; g++ evaluates them right to left, so the FIRST
+// draw becomes Xi.y and the second Xi.x (pinned against the compiled reference by the sample KAT).
+PT_HD f3 ggx_sample_draws(float first_draw, float second_draw, float alpha, f3 n) {
+    return ggx_sample(second_draw, first_draw, alpha, n);
+}
+
+PT_HD float mat_pdf(const Material &m, f3 wi, f3 wo, f3 N, int c, bool is_reflect) {  // pdf, :285-328
+    if (mat_is_rough(m)) {
+        f3 h;
+        float jac;
+        if (is_reflect) {
+            h = normalized(wi + wo);
+            h = (dot(wi, N) > 0) ? h : -h;
+            jac = 1.0f / (4.0f * fabsf(dot(h, wo)));
+        } else {
+            float ior = mat_ior(m, c);
+            float eta = (dot(wi, N) > 0) ? ior : (float)(1. / (double)ior);
+            f3 hv = (-wi) - wo * eta;
+            h = normalized(hv);
+            float d1 = dot(hv, hv);
+            jac = eta * eta * fabsf(dot(h, wo)) / d1;
+        }
+        float D = d_ggx(h, N, m.roughness);
+        return D * dot(N, h) * jac;
+    }
+    f3 h;
+    if (is_reflect) h = normalized(wi + wo);
+    else {
+        float ior = mat_ior(m, c);
+        float eta = (dot(wi, N) > 0) ? ior : (float)(1. / (double)ior);
+        h = normalized((-wi) - wo * eta);
+        h = dot(h, N) > 0 ? h : -h;
+    }
+    return (fabsf(dot(h, N)) > 1 - kEps) ? 1.0f : 0.0f;
+}
+
+PT_HD float mat_eval(const Material &m, f3 wi, f3 wo, f3 N, int c, float u, float v, bool is_reflect) {  // eval, :330-408
+    if (mat_is_rough(m)) {
+        if (is_reflect) {
+            if (dot(wi, N) * dot(wo, N) <= 0) return 0.f;
+            f3 h = normalized(wi + wo);
+            h = dot(wi, N) > 0 ? h : -h;
+            float F = (m.type == MAT_ROUGH_CONDUCTOR) ? fresnel_schlick(m, fabsf(dot(h, wo)), u, v, c) : mat_fresnel(m, -wi, h, c);
+            float D = d_ggx(h, N, m.roughness);
+            float G = g_ggx(wi, wo, h, m.roughness);
+            float denom = 4.0f * fabsf(dot(N, wi)) * fabsf(dot(N, wo)) + kEps;
+            return F * D * G / denom;
+        }
+        if (m.type == MAT_ROUGH_CONDUCTOR || dot(wi, N) * dot(wo, N) >= 0) return 0.f;
+        float ior = mat_ior(m, c);
+        float eta = (dot(wi, N) > 0) ? ior : (float)(1. / (double)ior);
+        f3 h = normalized((-wi) - wo * eta);
+        h = dot(h, N) > 0 ? h : -h;
+        float F = mat_fresnel(m, -wi, h, c);
+        float D = d_ggx(h, N, m.roughness);
+        float G = g_ggx(wi, wo, h, m.roughness);
+        float hol = dot(h, wi);
+        float hov = dot(h, wo);
+        float den = hol + eta * hov;
+        den *= den;
+        den *= fabsf(dot(N, wi) * dot(N, wo));
+        return (1.0f - F) * D * G * eta * eta * fabsf(hol * hov) / den;
+    }
+    if (is_reflect) {
+        f3 h = normalized(wi + wo);
+        h = (dot(wi, N) > 0) ? h : -h;
+        if (dot(wi, N) * dot(wo, N) <= 0 || dot(h, N) < 1 - kEps) return 0.f;
+        return (m.type == MAT_SMOOTH_CONDUCTOR) ? fresnel_schlick(m, fabsf(dot(N, wo)), u, v, c) : mat_fresnel(m, -wi, N, c);
+    }
+    float ior = mat_ior(m, c);
+    float eta = (dot(wi, N) > 0) ? ior : (float)(1. / (double)ior);
+    f3 h = normalized((-wi) - wo * eta);
+    h = (dot(h, N) > 0) ? h : -h;
+    if (m.type == MAT_SMOOTH_CONDUCTOR || dot(wi, N) * dot(wo, N) >= 0 || dot(h, N) < 1 - kEps) return 0.f;
+    return (float)(1. - (double)mat_fresnel(m, -wi, N, c));
+}
+
+// ---- Scene::sampleEnv, src/Scene.hpp:60-99 --------------------------------------------------------------------
+PT_HD f3 env_lookup(const SceneView &S, f3 dir) {
+    if (!S.use_env) return mk3(S.bg[0], S.bg[1], S.bg[2]);
+    f3 d = normalized(dir);
+    float phi = atan2f(d.z, d.x);
+    float theta = acosf(d.y);
+    float u = (phi + kPi) / (2.f * kPi);
+    float v = theta / kPi;
+    u = u - floorf(u);
+    v = (v < 0.f) ? 0.f : ((1.f < v) ? 1.f : v);  // std::clamp(v, 0.f, 1.f)
+    float x = u * (float)S.env_w - 0.5f;
+    float y = v * (float)S.env_h - 0.5f;
+    int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    int W = S.env_w, H = S.env_h;
+    int X0 = x0 % W; if (X0 < 0) X0 += W;
+    int X1 = (x0 + 1) % W; if (X1 < 0) X1 += W;
+    int Y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
+    int Y1 = (y0 + 1) < 0 ? 0 : ((y0 + 1) > H - 1 ? H - 1 : (y0 + 1));
+    float sx = x - x0, sy = y - y0;
+    f3 c00 = xyz(PT_LDG4(S.env + (size_t)Y0 * W + X0)), c10 = xyz(PT_LDG4(S.env + (size_t)Y0 * W + X1));
+    f3 c01 = xyz(PT_LDG4(S.env + (size_t)Y1 * W + X0)), c11 = xyz(PT_LDG4(S.env + (size_t)Y1 * W + X1));
+    f3 c0 = c00 * (1 - sx) + c10 * sx;
+    f3 c1 = c01 * (1 - sx) + c11 * sx;
+    return c0 * (1 - sy) + c1 * sy;
+}
+
+// ---- Scene::sampleLight -> MeshTriangle::Sample -> BVHAccel::Sample/getSample -> Triangle::Sample ---------------
+// src/Scene.cpp:23-37, src/Triangle.hpp:193-196,71-76, src/BVH.cpp:118-135.  u0..u3 in draw order.
+struct LightSample {
+    f3 p, n, emit;
+    float pdf;
+};
+PT_HD LightSample sample_light(const SceneView &S, float u0, float u1, float u2, float u3) {
+    LightSample ls;
+    ls.p = mk3(0, 0, 0); ls.n = mk3(0, 0, 0); ls.emit = mk3(0, 0, 0); ls.pdf = 1.f;
+    float sum = 0;
+    for (int i = 0; i < S.n_lights; ++i) sum += S.light_area[i];
+    float p = u0 * sum;
+    sum = 0;
+    for (int i = 0; i < S.n_lights; ++i) {
+        sum += S.light_area[i];
+        if (p <= sum) {
+            int node = (int)S.light_root[i];
+            float root_area = S.ln_area[node];
+            float q = sqrtf(u1) * root_area;  // BVHAccel::Sample: sqrt-warped selector
+            while (S.ln_left[node] >= 0 && S.ln_right[node] >= 0) {
+                int l = S.ln_left[node];
+                float la = S.ln_area[l];
+                if (q < la) node = l;
+                else { q = q - la; node = S.ln_right[node]; }
+            }
+            int prim = S.ln_prim[node];
+            f3 v0 = xyz(PT_LDG4(S.v0 + prim));
+            const float *w = S.v1v2 + 6 * (size_t)prim;
+            f3 v1 = mk3(w[0], w[1], w[2]), v2 = mk3(w[3], w[4], w[5]);
+            float4 nn = PT_LDG4(S.nrm + prim);
+            float x = sqrtf(u2), y = u3;  // Triangle::Sample
+            ls.p = (v0 * (1.0f - x) + v1 * (x * (1.0f - y))) + v2 * (x * y);
+            ls.n = xyz(nn);
+            float pdf = 1.0f / nn.w;
+            pdf *= S.ln_area[node];
+            pdf /= root_area;
+            ls.pdf = pdf;
+            const Material &lm = S.mats[S.light_mat[i]];
+            ls.emit = mk3(lm.emission[0], lm.emission[1], lm.emission[2]);
+            break;
+        }
+    }
+    return ls;
+}
+
+// ---- camera ray, src/Renderer.cpp:39-76 ------------------------------------------------------------------------
+struct Camera {
+    int width, height;
+    f3 eye;
+    float O[9];  // row-major, columns (left, new_up, forward)
+    float scale, aspect;
+    int use_dof;
+    float focal_distance, aperture_radius;
+};
+PT_HD f3 mat3_mul(const float *O, f3 v) {
+    return mk3(O[0] * v.x + (O[1] * v.y + O[2] * v.z), O[3] * v.x + (O[4] * v.y + O[5] * v.z), O[6] * v.x + (O[7] * v.y + O[8] * v.z));
+}
+PT_HD void camera_ray(const Camera &cam, int i, int j, Stream &rs, f3 *pos, f3 *dir) {
+    float x = (1 - 2 * (i + stream_next(rs)) / (float)cam.width) * cam.aspect * cam.scale;
+    float y = (1 - 2 * (j + stream_next(rs)) / (float)cam.height) * cam.scale;
+    if (cam.use_dof) {
+        f3 focal = mk3(x, y, 1) * cam.focal_distance;
+        float r = cam.aperture_radius * sqrtf(stream_next(rs));
+        float theta = 2 * kPi * stream_next(rs);
+        float st, ct;
+        sincos_portable(theta, &st, &ct);
+        float dx = r * ct, dy = r * st;
+        *pos = cam.eye + mat3_mul(cam.O, mk3(dx, dy, 0));
+        *dir = normalized(focal - mk3(dx, dy, 0));
+    } else {
+        *dir = normalized(mk3(x, y, 1));
+        *pos = cam.eye;
+    }
+    *dir = mat3_mul(cam.O, *dir);
+}
+
+// ---- one next-event sample of Scene::directLighting, src/Scene.cpp:63-80 ------------------------------------------
+// Returns the geometry of light sample i; the caller traces visibility and evaluates the term per channel.
+struct NeeGeom {
+    f3 ws, n_light, emit;
+    float dist, pdf;
+};
+PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u2, float u3) {
+    LightSample ls = sample_light(S, u0, u1, u2, u3);
+    NeeGeom g;
+    f3 d = ls.p - p;
+    g.ws = normalized(d);
+    g.dist = norm(d);
+    g.n_light = ls.n; g.emit = ls.emit; g.pdf = ls.pdf;
+    return g;
+}
+PT_HD float nee_term(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, float u, float v, bool is_reflect, int n_dir) {
+    float emit = comp(g.emit, c);
+    return emit * mat_eval(m, g.ws, wo, n, c, u, v, is_reflect) * dot(g.ws, n) * dot(-g.ws, g.n_light) / (g.dist * g.dist) / g.pdf /
+           n_dir;
+}
+
+}  // namespace pt

@@ -1,0 +1,81 @@
+// csrc/pt_pack.hpp — host-side repacking of a b2pt_scene_desc into the arrays a pt::SceneView
+// points at (materials with the hasEmission flag resolved, env texels padded to float4).
+// Plain C++: used by the CUDA library before its cudaMemcpy calls and by tests/hostcheck.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2pt.h"
+#include "pt_math.cuh"
+
+namespace pt {
+
+struct PackedScene {
+    std::vector<Material> mats;
+    std::vector<float4> env;
+};
+
+inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
+    if (!d) { err = "scene is NULL"; return false; }
+    if (d->n_nodes < 2 || (d->n_nodes & 1u) || !d->nodes) { err = "scene needs an even, non-zero number of nodes"; return false; }
+    if (d->n_prims == 0 || !d->prim_v0 || !d->prim_e1 || !d->prim_e2 || !d->prim_v1v2 || !d->prim_normal || !d->prim_uv ||
+        !d->prim_material || !d->prim_kind) { err = "scene primitive arrays missing"; return false; }
+    if (d->n_materials == 0 || d->n_materials > B2PT_MAX_MATERIALS || !d->materials) { err = "bad material table"; return false; }
+    if (d->n_lights > B2PT_MAX_LIGHTS) { err = "too many lights"; return false; }
+    if (d->max_depth + 2 >= (uint32_t)kStackSize) { err = "tree too deep for the traversal stack"; return false; }
+    if (d->use_env_map && (!d->env_rgb || d->env_width == 0 || d->env_height == 0)) { err = "env map enabled without texels"; return false; }
+    if (d->n_dir_sample < 1) { err = "n_dir_sample must be >= 1"; return false; }
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const b2pt_node &n = d->nodes[i];
+        if (n.kind == B2PT_NODE_INTERIOR) {
+            if (2 * (uint64_t)n.a + 1 >= d->n_nodes) { err = "node child index out of range"; return false; }
+        } else if (n.kind == B2PT_NODE_TRIANGLE || n.kind == B2PT_NODE_SPHERE) {
+            if (n.a >= d->n_prims) { err = "node primitive index out of range"; return false; }
+        } else if (n.kind != B2PT_NODE_EMPTY) { err = "bad node kind"; return false; }
+    }
+    for (uint32_t i = 0; i < d->n_prims; ++i)
+        if (d->prim_material[i] >= d->n_materials) { err = "primitive material index out of range"; return false; }
+    for (uint32_t i = 0; i < d->n_light_nodes; ++i) {
+        int l = d->light_node_left[i], r = d->light_node_right[i], p = d->light_node_prim[i];
+        if (l >= (int)d->n_light_nodes || r >= (int)d->n_light_nodes) { err = "light tree index out of range"; return false; }
+        if ((l < 0 || r < 0) && (p < 0 || p >= (int)d->n_prims)) { err = "light tree leaf without primitive"; return false; }
+    }
+    for (uint32_t i = 0; i < d->n_lights; ++i)
+        if (d->light_root[i] >= d->n_light_nodes || d->light_material[i] >= d->n_materials) { err = "bad light entry"; return false; }
+    return true;
+}
+
+inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out) {
+    out.mats.resize(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const b2pt_material &s = d->materials[i];
+        Material &m = out.mats[i];
+        m.type = s.type;
+        for (int c = 0; c < 3; ++c) { m.emission[c] = s.emission[c]; m.refl[c] = s.base_reflectance[c]; }
+        m.ior_a = s.ior_a; m.ior_b = s.ior_b; m.roughness = s.roughness;
+        m.textured = s.textured;
+        // Material::hasEmission: m_emission.norm() > EPSILON (src/Material.hpp:263)
+        float n2 = s.emission[0] * s.emission[0] + (s.emission[1] * s.emission[1] + s.emission[2] * s.emission[2]);
+        m.emissive = std::sqrt(n2) > kEps ? 1 : 0;
+    }
+    out.env.clear();
+    if (d->use_env_map) {
+        size_t n = (size_t)d->env_width * d->env_height;
+        out.env.resize(n);
+        for (size_t i = 0; i < n; ++i) out.env[i] = make_float4(d->env_rgb[3 * i], d->env_rgb[3 * i + 1], d->env_rgb[3 * i + 2], 0.f);
+    }
+}
+
+inline Camera make_camera(const b2pt_camera *c) {
+    Camera k;
+    k.width = c->width; k.height = c->height;
+    k.eye = mk3(c->position[0], c->position[1], c->position[2]);
+    for (int i = 0; i < 9; ++i) k.O[i] = c->orientation[i];
+    k.scale = c->scale; k.aspect = c->aspect;
+    k.use_dof = c->use_dof; k.focal_distance = c->focal_distance; k.aperture_radius = c->aperture_radius;
+    return k;
+}
+
+}  // namespace pt

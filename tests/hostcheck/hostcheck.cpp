@@ -1,0 +1,176 @@
+// tests/hostcheck/hostcheck.cpp — TEST INFRASTRUCTURE, not shipped.
+//
+// Compiles the device arithmetic of csrc/pt_math.cuh for the host with g++ so that the
+// `-m "not gpu"` tests can compare it with the oracle on a machine without a GPU (the same
+// functions are checked again on the device through the C ABI by the `-m gpu` tests).
+// Nothing in the package, bench.py or the RayTracing program links or loads this library.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2pt.h"
+#include "pt_math.cuh"
+#include "pt_pack.hpp"
+
+using namespace pt;
+
+struct HcScene {
+    PackedScene packed;
+    std::vector<float4> nodes, v0, e1, e2, nrm;
+    std::vector<float> v1v2, uv, light_area, ln_area;
+    std::vector<uint32_t> prim_mat, prim_kind, light_root, light_mat;
+    std::vector<int> ln_left, ln_right, ln_prim;
+    SceneView view;
+};
+static inline f3 V(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+extern "C" {
+
+void *hc_scene_new(const b2pt_scene_desc *d) {
+    std::string err;
+    if (!validate_scene(d, err)) return nullptr;
+    HcScene *h = new HcScene();
+    pack_scene(d, h->packed);
+    h->nodes.resize(2 * (size_t)d->n_nodes);
+    std::memcpy(h->nodes.data(), d->nodes, sizeof(b2pt_node) * d->n_nodes);
+    auto cp4 = [&](std::vector<float4> &dst, const float *src) { dst.resize(d->n_prims); std::memcpy(dst.data(), src, 16 * (size_t)d->n_prims); };
+    cp4(h->v0, d->prim_v0); cp4(h->e1, d->prim_e1); cp4(h->e2, d->prim_e2); cp4(h->nrm, d->prim_normal);
+    h->v1v2.assign(d->prim_v1v2, d->prim_v1v2 + 6 * (size_t)d->n_prims);
+    h->uv.assign(d->prim_uv, d->prim_uv + 6 * (size_t)d->n_prims);
+    h->prim_mat.assign(d->prim_material, d->prim_material + d->n_prims);
+    h->prim_kind.assign(d->prim_kind, d->prim_kind + d->n_prims);
+    h->light_area.assign(d->light_area, d->light_area + d->n_lights);
+    h->light_root.assign(d->light_root, d->light_root + d->n_lights);
+    h->light_mat.assign(d->light_material, d->light_material + d->n_lights);
+    h->ln_area.assign(d->light_node_area, d->light_node_area + d->n_light_nodes);
+    h->ln_left.assign(d->light_node_left, d->light_node_left + d->n_light_nodes);
+    h->ln_right.assign(d->light_node_right, d->light_node_right + d->n_light_nodes);
+    h->ln_prim.assign(d->light_node_prim, d->light_node_prim + d->n_light_nodes);
+    SceneView &v = h->view;
+    v.nodes = h->nodes.data(); v.v0 = h->v0.data(); v.e1 = h->e1.data(); v.e2 = h->e2.data(); v.nrm = h->nrm.data();
+    v.v1v2 = h->v1v2.data(); v.uv = h->uv.data(); v.prim_mat = h->prim_mat.data(); v.prim_kind = h->prim_kind.data();
+    v.mats = h->packed.mats.data();
+    v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
+    v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
+    v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height; v.env = h->packed.env.data();
+    for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
+    v.rr_rate = d->rr_rate; v.inv_rr = d->inv_rr; v.enable_shadow = d->enable_shadow; v.n_dir = d->n_dir_sample;
+    return h;
+}
+void hc_scene_free(void *h) { delete (HcScene *)h; }
+
+void hc_intersect(void *h, const float *o, const float *d, long n, int *prim, double *t, unsigned long long *counts) {
+    const SceneView &S = ((HcScene *)h)->view;
+    unsigned long long nodes = 0, prims = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, prims)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        Hit hit = closest_hit<true>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), &st);
+        prim[i] = hit.prim; t[i] = hit.t;
+        nodes += st.nodes; prims += st.prims;
+    }
+    if (counts) { counts[0] = nodes; counts[1] = prims; }
+}
+void hc_shadow(void *h, const float *o, const float *d, const float *dist, long n, int *visible) {
+    const SceneView &S = ((HcScene *)h)->view;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st) ? 1 : 0;
+    }
+}
+void hc_surface(void *h, const float *o, const float *d, long n, float *coords, float *normal, float *uv) {
+    const SceneView &S = ((HcScene *)h)->view;
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
+        Hit hit = closest_hit<false>(S, r, &st);
+        if (hit.prim < 0) continue;
+        Surface s = surface_at(S, r, hit);
+        coords[3 * i] = s.p.x; coords[3 * i + 1] = s.p.y; coords[3 * i + 2] = s.p.z;
+        normal[3 * i] = s.n.x; normal[3 * i + 1] = s.n.y; normal[3 * i + 2] = s.n.z;
+        uv[2 * i] = s.u; uv[2 * i + 1] = s.v;
+    }
+}
+void hc_tri(const float *v9, const float *o, const float *d, long n, int *hit, double *t) {
+    for (long i = 0; i < n; ++i) {
+        f3 v0 = V(v9 + 9 * i), v1 = V(v9 + 9 * i + 3), v2 = V(v9 + 9 * i + 6);
+        double tt = 1.7976931348623157e308, u, v;
+        hit[i] = tri_hit(v0, v1 - v0, v2 - v0, make_ray(V(o + 3 * i), V(d + 3 * i)), &tt, &u, &v) ? 1 : 0;
+        t[i] = tt;
+    }
+}
+void hc_box(const float *b6, const float *o, const float *d, long n, int *hit) {
+    for (long i = 0; i < n; ++i) {
+        float tm;
+        hit[i] = box_hit(V(b6 + 6 * i), V(b6 + 6 * i + 3), make_ray(V(o + 3 * i), V(d + 3 * i)), &tm) ? 1 : 0;
+    }
+}
+void hc_sphere(const float *c4, const float *o, const float *d, long n, int *hit, double *t) {
+    for (long i = 0; i < n; ++i) {
+        float tf = 0.f;
+        float r = c4[4 * i + 3];
+        bool ok = sphere_hit(V(c4 + 4 * i), r * r, make_ray(V(o + 3 * i), V(d + 3 * i)), &tf);
+        hit[i] = ok; t[i] = ok ? (double)tf : 1.7976931348623157e308;
+    }
+}
+void hc_eval(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const float *uv, const int *refl, long n, float *out) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    for (long i = 0; i < n; ++i) out[i] = mat_eval(m, V(wi + 3 * i), V(wo + 3 * i), V(N + 3 * i), wl[i], uv[2 * i], uv[2 * i + 1], refl[i] != 0);
+}
+void hc_pdf(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *refl, long n, float *out) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    for (long i = 0; i < n; ++i) out[i] = mat_pdf(m, V(wi + 3 * i), V(wo + 3 * i), V(N + 3 * i), wl[i], refl[i] != 0);
+}
+void hc_fresnel(void *h, int mat, const float *I, const float *N, const int *wl, long n, float *out) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    for (long i = 0; i < n; ++i) out[i] = mat_fresnel(m, V(I + 3 * i), V(N + 3 * i), wl[i]);
+}
+void hc_refract(void *h, int mat, const float *I, const float *N, const int *wl, long n, float *out3) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    for (long i = 0; i < n; ++i) { f3 r = mat_refract(m, V(I + 3 * i), V(N + 3 * i), wl[i]); out3[3 * i] = r.x; out3[3 * i + 1] = r.y; out3[3 * i + 2] = r.z; }
+}
+void hc_reflect(const float *I, const float *N, long n, float *out3) {
+    for (long i = 0; i < n; ++i) { f3 r = mat_reflect(V(I + 3 * i), V(N + 3 * i)); out3[3 * i] = r.x; out3[3 * i + 1] = r.y; out3[3 * i + 2] = r.z; }
+}
+// u2 in DRAW order; the mapping of draws to Xi.x / Xi.y is the library's (see pt_kernels.cu: sample_normal).
+void hc_material_sample(void *h, int mat, const float *N, const float *u2, long n, float *out3) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    for (long i = 0; i < n; ++i) {
+        f3 r = mat_is_rough(m) ? ggx_sample_draws(u2[2 * i], u2[2 * i + 1], m.roughness, V(N + 3 * i)) : V(N + 3 * i);
+        out3[3 * i] = r.x; out3[3 * i + 1] = r.y; out3[3 * i + 2] = r.z;
+    }
+}
+void hc_env(void *h, const float *d, long n, float *rgb) {
+    const SceneView &S = ((HcScene *)h)->view;
+    for (long i = 0; i < n; ++i) { f3 c = env_lookup(S, V(d + 3 * i)); rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z; }
+}
+void hc_sample_light(void *h, const float *u4, long n, float *coords, float *normal, float *emit, float *pdf) {
+    const SceneView &S = ((HcScene *)h)->view;
+    for (long i = 0; i < n; ++i) {
+        LightSample ls = sample_light(S, u4[4 * i], u4[4 * i + 1], u4[4 * i + 2], u4[4 * i + 3]);
+        coords[3 * i] = ls.p.x; coords[3 * i + 1] = ls.p.y; coords[3 * i + 2] = ls.p.z;
+        normal[3 * i] = ls.n.x; normal[3 * i + 1] = ls.n.y; normal[3 * i + 2] = ls.n.z;
+        emit[3 * i] = ls.emit.x; emit[3 * i + 1] = ls.emit.y; emit[3 * i + 2] = ls.emit.z;
+        pdf[i] = ls.pdf;
+    }
+}
+void hc_camera_rays(const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count, unsigned long long seed,
+                    float *o, float *d) {
+    Camera c = make_camera(cam);
+    for (int q = 0; q < npix; ++q)
+        for (int k = 0; k < sample_count; ++k) {
+            int m = pixels[q];
+            Stream rs = stream_open((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)m, (uint32_t)(sample_begin + k), STREAM_CAMERA, 0);
+            f3 pos, dir;
+            camera_ray(c, m % c.width, m / c.width, rs, &pos, &dir);
+            size_t e = (size_t)q * sample_count + k;
+            o[3 * e] = pos.x; o[3 * e + 1] = pos.y; o[3 * e + 2] = pos.z;
+            d[3 * e] = dir.x; d[3 * e + 1] = dir.y; d[3 * e + 2] = dir.z;
+        }
+}
+void hc_stream_uniforms(unsigned long long seed, unsigned pixel, unsigned sample, unsigned tag, unsigned dim_begin, int count, float *out) {
+    Stream rs = stream_open((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, tag, dim_begin);
+    for (int i = 0; i < count; ++i) out[i] = stream_next(rs);
+}
+}
