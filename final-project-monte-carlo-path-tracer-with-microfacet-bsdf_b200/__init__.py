@@ -74,7 +74,8 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
                 ("bundles", C.c_uint64), ("paths", C.c_uint64), ("rays_traced_closest", C.c_uint64),
                 ("rays_traced_shadow", C.c_uint64), ("rays_reference", C.c_uint64), ("nodes_fetched", C.c_uint64),
-                ("prims_tested", C.c_uint64), ("vertices_shaded", C.c_uint64), ("max_depth", C.c_uint32), ("waves", C.c_uint32)]
+                ("prims_tested", C.c_uint64), ("extend_nodes", C.c_uint64), ("extend_prims", C.c_uint64),
+                ("shadow_nodes", C.c_uint64), ("shadow_prims", C.c_uint64), ("vertices_shaded", C.c_uint64), ("max_depth", C.c_uint32), ("waves", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -183,6 +184,7 @@ def gpu_lib():
         L.b2pt_last_error.argtypes = [C.c_void_p]
         L.b2pt_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.b2pt_destroy.argtypes = [C.c_void_p]
+        L.b2pt_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2pt_upload_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
         L.b2pt_update_scene_params.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
         rp, st = C.POINTER(RenderParams), C.POINTER(Stats)
@@ -409,6 +411,10 @@ class Context:
     def _ck(self, r):
         if r != 0:
             raise RuntimeError(f"b2pt error {r}: " + self.L.b2pt_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream=None):
+        """Issue work on `cuda_stream` (an int cudaStream_t handle, 0 = default stream); None = the context's own stream."""
+        self._ck(self.L.b2pt_set_stream(self.h, C.c_void_p(cuda_stream or 0), 0 if cuda_stream is None else 1))
 
     def upload(self, scene: HostScene):
         self._ck(self.L.b2pt_upload_scene(self.h, C.byref(scene.desc)))

@@ -1,0 +1,1273 @@
+// csrc/pt_kernels.cu — the CUDA wavefront path tracer behind include/b2pt.h (sm_100a only).
+//
+// Replaces the OpenMP pixel loop of Renderer::Render (src/Renderer.cpp:36-92) and everything
+// below it (Scene::castRay, src/Scene.cpp:85-184).  The recursion of castRay is unrolled into
+// waves of rays that move through five kernels per bounce:
+//
+//   generate   camera rays of a wave of pixel-samples                 (Renderer.cpp:39-76)
+//   extend     closest hit of every queued ray                        (Scene::intersect)
+//   light      next-event shadow rays of every surviving vertex       (Scene::directLighting, ray part)
+//   shadow     visibility of every shadow ray                         (Scene.cpp:72-75)
+//   shade      the rest of castRay for one vertex: terminal cases, microfacet normal, Fresnel,
+//              direct light, Russian roulette, reflect/refract choice, continuation rays
+//
+// A queued ray carries up to three wavelength paths (R, G, B: Renderer.cpp:77-79) that still
+// share their geometry; they read the same sample stream, so they stay together until a
+// dielectric refracts them apart (Cauchy dispersion) or their Fresnel choices differ, at
+// which point `shade` emits one continuation ray per distinct direction.  The per-level
+// clamps of castRay (Scene.cpp:180-183) are carried as a clamped-affine map per path
+//  instead of a recursion stack.
+//
+// Queues are SoA float4 arrays compacted with __ballot_sync/__popc warp scans; counts stay on
+// the device, the host reads one counter per bounce to know when a wave has drained.
+// There is no CPU path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2pt.h"
+#include "pt_math.cuh"
+#include "pt_pack.hpp"
+
+using namespace pt;
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr uint32_t kNoShadow = 0xFFFFFFFFu;
+constexpr uint32_t INFO_DIM_MASK = 0xFFFFFu;  // bits 0-19: next draw of the path stream
+constexpr int INFO_MASK_SHIFT = 20;            // bits 20-22: wavelength paths on this ray
+constexpr uint32_t INFO_PRIMARY = 1u << 23;    // depth == 0
+constexpr int INFO_DEPTH_SHIFT = 24;           // bits 24-31: depth (saturating, statistics only)
+
+thread_local std::string g_create_error;
+
+// ---- device counters ---------------------------------------------------------------------------
+struct Counters {
+    unsigned int n_cur, n_next, n_shadow, pad;
+    unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
+    unsigned int max_depth, pad2;
+};
+
+// ---- ray queue (SoA) -----------------------------------------------------------------------------
+struct Queue {
+    float4 *o;       // origin.xyz, w = pixel index (bits)
+    float4 *d;       // direction.xyz, w = global sample index (bits)
+    uint32_t *slot;  // accumulation slot (pixel, or row of the per-sample output)
+    uint32_t *info;  // INFO_* fields
+    float4 *chan;    // [(c*2 + k) * cap + i]: k=0 (M, K, L, U) of the path's clamped-affine map,
+                     //                         k=1 (A, eval, f, 0) of the level still waiting for its probe ray
+    size_t cap;
+};
+
+struct WaveBufs {
+    Queue q[2];
+    int *hit_prim;
+    float *hit_t;
+    uint32_t *sh_base;
+    float4 *sh_o;  // origin.xyz, w = dist
+    float4 *sh_d;  // direction.xyz
+    unsigned char *vis;
+};
+
+struct GenParams {
+    int mode;  // 0 frame, 1 listed pixels
+    unsigned long long first;
+    unsigned int count;
+    int width, height, tiles_x;
+    unsigned int frame_slots;
+    int sample_begin, sample_count;
+    const int *pixels;
+    uint32_t k0, k1;
+    int split;
+};
+
+struct ShadeParams {
+    uint32_t k0, k1;
+    float div;  // spp_total as float: framebuffer += rgb / spp (Renderer.cpp:80)
+    float *acc;
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- clamped-affine path state ------------------------------------------------
+struct Phi {
+    float M, K, L, U;
+};
+__device__ __forceinline__ bool phi_unbounded(const Phi &p) { return !(p.L > -INFINITY) && !(p.U < INFINITY); }
+__device__ __forceinline__ float phi_clamp(const Phi &p, float y) { return phi_unbounded(p) ? y : clamp_ref(p.L, p.U, y); }
+__device__ __forceinline__ float phi_apply(const Phi &p, float x) { return phi_clamp(p, p.M * x + p.K); }
+// phi o g with g(x) = A + clamp(0, 5, f * x): one non-terminal level of castRay (Scene.cpp:139-143,180-183).
+__device__ __forceinline__ Phi phi_compose(const Phi &p, float A, float f) {
+    float c = p.M * A + p.K, c5 = p.M * (A + 5.f) + p.K;
+    float b0 = phi_clamp(p, c), b1 = phi_clamp(p, c5);
+    Phi r;
+    if (f != f || f == INFINITY) {  // clamp(0, 5, NaN) = 5: the level is the constant A + 5
+        r.M = 0.f; r.K = b1; r.L = b1; r.U = b1;
+    } else if (f == -INFINITY) {
+        r.M = 0.f; r.K = b0; r.L = b0; r.U = b0;
+    } else {
+        r.M = p.M * f; r.K = c;
+        r.L = fminf(b0, b1); r.U = fmaxf(b0, b1);
+    }
+    return r;
+}
+
+// ---- generate: Renderer.cpp:39-76 -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams gp, Queue q, Counters *cnt) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long rounded = ((unsigned long long)gp.count + kBlock - 1) / kBlock * kBlock;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * kBlock; it < rounded; it += (unsigned long long)gridDim.x * kBlock) {
+        unsigned long long li = it + threadIdx.x;
+        bool valid = li < gp.count;
+        unsigned long long gi = gp.first + li;
+        uint32_t pixel = 0, sample = 0, slot = 0;
+        if (valid) {
+            if (gp.mode == 0) {
+                unsigned long long s = gi / gp.frame_slots;
+                uint32_t r = (uint32_t)(gi % gp.frame_slots);
+                uint32_t tile = r >> 5, l = r & 31u;
+                int x = (int)(tile % gp.tiles_x) * 8 + (int)(l & 7u);
+                int y = (int)(tile / gp.tiles_x) * 4 + (int)(l >> 3);
+                valid = x < gp.width && y < gp.height;
+                pixel = (uint32_t)(y * gp.width + x);
+                sample = (uint32_t)(gp.sample_begin + (int)s);
+                slot = pixel;
+            } else {
+                uint32_t qi = (uint32_t)(gi / (unsigned)gp.sample_count), k = (uint32_t)(gi % (unsigned)gp.sample_count);
+                pixel = (uint32_t)gp.pixels[qi];
+                sample = (uint32_t)(gp.sample_begin + (int)k);
+                slot = (uint32_t)gi;
+            }
+        }
+        f3 pos = mk3(0, 0, 0), dir = mk3(0, 0, 1);
+        if (valid) {
+            Stream rs = stream_open(gp.k0, gp.k1, pixel, sample, STREAM_CAMERA, 0);
+            camera_ray(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), rs, &pos, &dir);
+        }
+        const int per = gp.split ? 3 : 1;
+        unsigned ballot = __ballot_sync(0xffffffffu, valid);
+        unsigned base = 0;
+        if (lane == 0 && ballot) base = atomicAdd(&cnt->n_next, (unsigned)(__popc(ballot) * per));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (valid) {
+            unsigned p = base + (unsigned)__popc(ballot & lanemask_lt()) * per;
+            for (int k = 0; k < per; ++k) {
+                uint32_t mask = gp.split ? (1u << k) : 7u;
+                q.o[p + k] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
+                q.d[p + k] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample));
+                q.slot[p + k] = slot;
+                q.info[p + k] = INFO_PRIMARY | (mask << INFO_MASK_SHIFT);
+            }
+        }
+    }
+}
+
+// ---- extend: Scene::intersect for every queued ray ---------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
+                                                        const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
+                                                        int *__restrict__ hit_prim, float *__restrict__ hit_t, Counters *cnt) {
+    const unsigned n = *n_ptr;
+    unsigned long long nodes = 0, prims = 0, refs = 0;
+    for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        float4 o = qo[i], d = qd[i];
+        Ray r = make_ray(xyz(o), xyz(d));
+        TravStats st{0, 0};
+        Hit h = closest_hit<COUNT>(S, r, &st);
+        hit_prim[i] = h.prim;
+        hit_t[i] = (float)h.t;  // Ray::operator()(double t) converts t to float before use
+        if (COUNT) { nodes += st.nodes; prims += st.prims; }
+        refs += (unsigned)__popc((qinfo[i] >> INFO_MASK_SHIFT) & 7u);
+    }
+    refs = warp_sum(refs);
+    if (COUNT) { nodes = warp_sum(nodes); prims = warp_sum(prims); }
+    if ((threadIdx.x & 31) == 0) {
+        if (refs) atomicAdd(&cnt->rays_reference, refs);
+        if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
+    }
+}
+
+// Geometry of the hit the shading kernels need (Intersection::coords / normal).
+__device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int prim, float tf, f3 *p, f3 *n, uint32_t *mat, uint32_t *kind) {
+    *mat = PT_LDG(S.prim_mat + prim);
+    *kind = PT_LDG(S.prim_kind + prim);
+    *p = r.o + r.d * tf;
+    if (*kind == NODE_TRIANGLE) *n = xyz(PT_LDG4(S.nrm + prim));
+    else *n = normalized(*p - xyz(PT_LDG4(S.v0 + prim)));
+}
+
+// ---- light: the shadow rays of Scene::directLighting (Scene.cpp:63-73) ---------------------------------------
+__global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
+                                                       const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ sh_o,
+                                                       float4 *__restrict__ sh_d, Counters *cnt, uint32_t k0, uint32_t k1) {
+    const unsigned n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
+    const unsigned ndir = (unsigned)S.n_dir;
+    unsigned long long refs = 0;
+    for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
+        unsigned i = it + threadIdx.x;
+        bool want = false;
+        Ray r;
+        f3 p, nn;
+        uint32_t info = 0, mat = 0, kind = 0;
+        float4 o4, d4;
+        if (i < n) {
+            int prim = hit_prim[i];
+            if (prim >= 0) {
+                o4 = q.o[i]; d4 = q.d[i]; info = q.info[i];
+                r.o = xyz(o4); r.d = xyz(d4);
+                hit_point(S, r, prim, hit_t[i], &p, &nn, &mat, &kind);
+                want = !S.mats[mat].emissive && S.enable_shadow;
+            }
+        }
+        unsigned ballot = __ballot_sync(0xffffffffu, want);
+        unsigned base = 0;
+        if (lane == 0 && ballot) base = atomicAdd(&cnt->n_shadow, (unsigned)__popc(ballot) * ndir);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (i < n) sh_base[i] = want ? base + (unsigned)__popc(ballot & lanemask_lt()) * ndir : kNoShadow;
+        if (want) {
+            unsigned b = base + (unsigned)__popc(ballot & lanemask_lt()) * ndir;
+            f3 pn = p + nn * kEps;  // inter.coords += n * EPSILON, Scene.cpp:114
+            uint32_t dim = (info & INFO_DIM_MASK) + (mat_is_rough(S.mats[mat]) ? 2u : 0u);
+            Stream rs = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), STREAM_PATH, dim);
+            for (unsigned k = 0; k < ndir; ++k) {
+                float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
+                NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
+                sh_o[b + k] = make_float4(pn.x, pn.y, pn.z, g.dist);
+                sh_d[b + k] = make_float4(g.ws.x, g.ws.y, g.ws.z, 0.f);
+            }
+            refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
+        }
+    }
+    refs = warp_sum(refs);
+    if (lane == 0 && refs) atomicAdd(&cnt->rays_reference, refs);
+}
+
+// ---- shadow: the visibility decision of Scene.cpp:72-75 -----------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
+                                                        const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis, Counters *cnt) {
+    const unsigned n = *n_ptr;
+    unsigned long long nodes = 0, prims = 0;
+    for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        float4 o = sh_o[i], d = sh_d[i];
+        Ray r = make_ray(xyz(o), xyz(d));
+        TravStats st{0, 0};
+        vis[i] = light_visible<COUNT>(S, r, o.w, &st) ? 1 : 0;
+        if (COUNT) { nodes += st.nodes; prims += st.prims; }
+    }
+    if (COUNT) {
+        nodes = warp_sum(nodes); prims = warp_sum(prims);
+        if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
+    }
+}
+
+// ---- shade: one vertex of Scene::castRay (Scene.cpp:85-184) ----------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Queue qo, const unsigned *__restrict__ n_ptr,
+                                                       const int *__restrict__ hit_prim, const float *__restrict__ hit_t,
+                                                       const uint32_t *__restrict__ sh_base, const unsigned char *__restrict__ vis,
+                                                       Counters *cnt, ShadeParams sp) {
+    const unsigned n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
+    const int ndir = S.n_dir;
+    unsigned long long verts = 0;
+    unsigned maxd = 0;
+    for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
+        const unsigned i = it + threadIdx.x;
+        int n_emit = 0;
+        // continuation rays this lane emits (at most one per wavelength path)
+        f3 e_o[3], e_d[3];
+        uint32_t e_mask[3] = {0, 0, 0};
+        Phi phi[3];
+        float lvl_A[3], lvl_e[3], lvl_f[3];
+        uint32_t pixel = 0, sample = 0, slot = 0, new_info = 0;
+
+        if (i < n) {
+            const float4 o4 = qi.o[i], d4 = qi.d[i];
+            const uint32_t info = qi.info[i];
+            pixel = __float_as_uint(o4.w); sample = __float_as_uint(d4.w); slot = qi.slot[i];
+            const uint32_t mask = (info >> INFO_MASK_SHIFT) & 7u;
+            const bool primary = (info & INFO_PRIMARY) != 0;
+            const uint32_t depth = info >> INFO_DEPTH_SHIFT;
+            Ray r;
+            r.o = xyz(o4); r.d = xyz(d4);
+            const int prim = hit_prim[i];
+            float *acc = sp.acc + 3 * (size_t)slot;
+
+            // state carried by the ray: the path map and the level whose probe ray this is
+            float pend_A[3] = {0, 0, 0}, pend_e[3] = {0, 0, 0}, pend_f[3] = {0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                phi[c].M = 1.f; phi[c].K = 0.f; phi[c].L = -INFINITY; phi[c].U = INFINITY;
+                if (!primary && (mask >> c & 1u)) {
+                    float4 a = qi.chan[(size_t)(c * 2) * qi.cap + i], b = qi.chan[(size_t)(c * 2 + 1) * qi.cap + i];
+                    phi[c].M = a.x; phi[c].K = a.y; phi[c].L = a.z; phi[c].U = a.w;
+                    pend_A[c] = b.x; pend_e[c] = b.y; pend_f[c] = b.z;
+                }
+            }
+
+            Material m;
+            Surface s;
+            bool terminal = prim < 0;
+            if (!terminal) {
+                Hit h; h.prim = prim; h.t = (double)hit_t[i];
+                s = surface_at(S, r, h);
+                m = S.mats[s.mat];
+                terminal = m.emissive != 0;
+            }
+            const f3 wo = -r.d;
+            if (terminal) {
+                // miss -> env (Scene.cpp:88-95); depth 0 emitter -> clamp(0,1,Le|wo.n|) (Scene.cpp:102-107);
+                // a probe ray that misses or hits an emitter -> env term of Scene.cpp:145-148,172-175.
+                f3 env = mk3(0, 0, 0);
+                if (!primary || prim < 0) env = env_lookup(S, r.d);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (!(mask >> c & 1u)) continue;
+                    float v;
+                    if (primary) v = (prim < 0) ? comp(env, c) : clamp_ref(0.f, 1.f, m.emission[c] * fabsf(dot(wo, s.n)));
+                    else v = phi_apply(phi[c], pend_A[c] + clamp_ref(0.f, 5.f, (comp(env, c) * pend_e[c]) * S.inv_rr));
+                    atomicAdd(acc + c, v / sp.div);
+                }
+            } else {
+                verts += (unsigned)__popc(mask);
+                if (depth > maxd) maxd = depth;
+                if (!primary) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (mask >> c & 1u) phi[c] = phi_compose(phi[c], pend_A[c], pend_f[c]);
+                }
+                const f3 nrm = s.n;
+                const bool rough = mat_is_rough(m);
+                Stream rs = stream_open(sp.k0, sp.k1, pixel, sample, STREAM_PATH, info & INFO_DIM_MASK);
+                f3 mfn = nrm;  // Material::sample, Material.hpp:268-281
+                if (rough) {
+                    float a = stream_next(rs), b = stream_next(rs);
+                    mfn = ggx_sample_draws(a, b, m.roughness, nrm);
+                }
+                float kr[3], ldir[3] = {0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) kr[c] = (mask >> c & 1u) ? mat_fresnel(m, r.d, mfn, c) : 0.f;
+                // direct light, Scene.cpp:56-82,114-119
+                const bool inner = dot(wo, nrm) < 0;
+                const f3 pn = s.p + nrm * kEps;
+                const uint32_t sb = sh_base[i];
+                for (int k = 0; k < ndir; ++k) {
+                    float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
+                    bool lit = !S.enable_shadow || (sb != kNoShadow && vis[sb + k]);
+                    if (!lit) continue;
+                    NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (mask >> c & 1u) ldir[c] += nee_term(m, g, wo, nrm, c, s.u, s.v, !inner, ndir);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    ldir[c] = inner ? (float)((1. - (double)kr[c]) * (double)ldir[c]) : kr[c] * ldir[c];
+
+                const float rr = stream_next(rs), rd = stream_next(rs);
+                const uint32_t new_dim = rs.dim;
+                if (rr >= S.rr_rate) {  // Scene.cpp:129-131,156-158: the raw l_dir is returned
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (mask >> c & 1u) atomicAdd(acc + c, phi_apply(phi[c], ldir[c]) / sp.div);
+                } else {
+                    const bool back = dot(wo, mfn) < 0;
+                    const bool dirac = !rough;
+                    const float cosn = fabsf(dot(wo, nrm));
+                    const f3 p_refl = back ? s.p - nrm * kEps : s.p + nrm * kEps;  // Scene.cpp:124-128
+                    const f3 p_refr = back ? s.p + nrm * kEps : s.p - nrm * kEps;  // Scene.cpp:151-155
+                    const f3 wi_refl = mat_reflect(wo, mfn);
+                    f3 wi[3];
+                    bool refl[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        refl[c] = rd < kr[c];
+                        wi[c] = wi_refl;
+                        if ((mask >> c & 1u) && !refl[c]) wi[c] = mat_refract(m, r.d, mfn, c);
+                    }
+                    uint32_t done = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (!(mask >> c & 1u) || (done >> c & 1u)) continue;
+                        uint32_t gm = 1u << c;
+#pragma unroll
+                        for (int c2 = c + 1; c2 < 3; ++c2) {
+                            if (!(mask >> c2 & 1u) || (done >> c2 & 1u) || refl[c2] != refl[c]) continue;
+                            if (refl[c] || (f2u(wi[c2].x) == f2u(wi[c].x) && f2u(wi[c2].y) == f2u(wi[c].y) && f2u(wi[c2].z) == f2u(wi[c].z)))
+                                gm |= 1u << c2;
+                        }
+                        done |= gm;
+                        e_o[n_emit] = refl[c] ? p_refl : p_refr;
+                        e_d[n_emit] = wi[c];
+                        e_mask[n_emit] = gm;
+                        n_emit++;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (!(mask >> c & 1u)) continue;
+                        float ev = mat_eval(m, wi[c], wo, nrm, c, s.u, s.v, refl[c]);
+                        float f;
+                        if (dirac) f = ev * S.inv_rr;
+                        else f = ((ev * cosn) / mat_pdf(m, wi[c], wo, nrm, c, refl[c])) * S.inv_rr;
+                        lvl_A[c] = clamp_ref(0.f, 15.f, ldir[c]);
+                        lvl_e[c] = ev;
+                        lvl_f[c] = f;
+                    }
+                    uint32_t nd = depth < 255u ? depth + 1u : 255u;
+                    new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT);
+                }
+            }
+        }
+        // append the continuation rays: warp scan over "emits >= 1 / 2 / 3 rays"
+        unsigned b1 = __ballot_sync(0xffffffffu, n_emit >= 1), b2 = __ballot_sync(0xffffffffu, n_emit >= 2),
+                 b3 = __ballot_sync(0xffffffffu, n_emit >= 3);
+        unsigned total = (unsigned)(__popc(b1) + __popc(b2) + __popc(b3));
+        unsigned base = 0;
+        if (lane == 0 && total) base = atomicAdd(&cnt->n_next, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (n_emit > 0) {
+            unsigned lt = lanemask_lt();
+            unsigned p = base + (unsigned)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt));
+            for (int k = 0; k < n_emit; ++k) {
+                qo.o[p + k] = make_float4(e_o[k].x, e_o[k].y, e_o[k].z, __uint_as_float(pixel));
+                qo.d[p + k] = make_float4(e_d[k].x, e_d[k].y, e_d[k].z, __uint_as_float(sample));
+                qo.slot[p + k] = slot;
+                qo.info[p + k] = new_info | (e_mask[k] << INFO_MASK_SHIFT);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (!(e_mask[k] >> c & 1u)) continue;
+                    qo.chan[(size_t)(c * 2) * qo.cap + p + k] = make_float4(phi[c].M, phi[c].K, phi[c].L, phi[c].U);
+                    qo.chan[(size_t)(c * 2 + 1) * qo.cap + p + k] = make_float4(lvl_A[c], lvl_e[c], lvl_f[c], 0.f);
+                }
+            }
+        }
+    }
+    verts = warp_sum(verts);
+    for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+    if (lane == 0) {
+        if (verts) atomicAdd(&cnt->vertices, verts);
+        if (maxd) atomicMax(&cnt->max_depth, maxd);
+    }
+}
+
+__global__ void swap_counts_kernel(Counters *cnt) {
+    cnt->rays_closest += cnt->n_cur;
+    cnt->rays_shadow += cnt->n_shadow;
+    cnt->n_cur = cnt->n_next;
+    cnt->n_next = 0;
+    cnt->n_shadow = 0;
+}
+
+// ---- batch kernels for the parity entry points ---------------------------------------------------------------
+__device__ __forceinline__ f3 ld3(const float *p, long long i) { return mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+__device__ __forceinline__ void st3(float *p, long long i, f3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+#define BATCH_INDEX(n)                                                      \
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;          \
+    if (i >= (n)) return;
+
+template <bool COUNT>
+__global__ void k_intersect(SceneView S, const float *o, const float *d, long long n, int *prim, double *t, Counters *cnt) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long nodes = 0, prims = 0;
+    if (i < n) {
+        TravStats st{0, 0};
+        Hit h = closest_hit<COUNT>(S, make_ray(ld3(o, i), ld3(d, i)), &st);
+        prim[i] = h.prim; t[i] = h.t;
+        nodes = st.nodes; prims = st.prims;
+    }
+    if (COUNT) {
+        nodes = warp_sum(nodes); prims = warp_sum(prims);
+        if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
+    }
+}
+__global__ void k_shadow(SceneView S, const float *o, const float *d, const float *dist, long long n, int *visible) {
+    BATCH_INDEX(n)
+    TravStats st{0, 0};
+    visible[i] = light_visible<false>(S, make_ray(ld3(o, i), ld3(d, i)), dist[i], &st) ? 1 : 0;
+}
+__global__ void k_tri(const float *v9, const float *o, const float *d, long long n, int *hit, double *t) {
+    BATCH_INDEX(n)
+    f3 v0 = ld3(v9, 3 * i), v1 = ld3(v9, 3 * i + 1), v2 = ld3(v9, 3 * i + 2);
+    double tt = 1.7976931348623157e308, u, v;
+    hit[i] = tri_hit(v0, v1 - v0, v2 - v0, make_ray(ld3(o, i), ld3(d, i)), &tt, &u, &v) ? 1 : 0;
+    t[i] = tt;
+}
+__global__ void k_box(const float *b6, const float *o, const float *d, long long n, int *hit) {
+    BATCH_INDEX(n)
+    float tm;
+    hit[i] = box_hit(ld3(b6, 2 * i), ld3(b6, 2 * i + 1), make_ray(ld3(o, i), ld3(d, i)), &tm) ? 1 : 0;
+}
+__global__ void k_sphere(const float *c4, const float *o, const float *d, long long n, int *hit, double *t, float *coords, float *normal) {
+    BATCH_INDEX(n)
+    f3 c = mk3(c4[4 * i], c4[4 * i + 1], c4[4 * i + 2]);
+    float rad = c4[4 * i + 3], tf = 0.f;
+    Ray r = make_ray(ld3(o, i), ld3(d, i));
+    bool ok = sphere_hit(c, rad * rad, r, &tf);
+    hit[i] = ok ? 1 : 0;
+    t[i] = ok ? (double)tf : 1.7976931348623157e308;
+    f3 p = mk3(0, 0, 0), nn = mk3(0, 0, 0);
+    if (ok) { p = r.o + r.d * tf; nn = normalized(p - c); }
+    st3(coords, i, p); st3(normal, i, nn);
+}
+__global__ void k_eval(SceneView S, int mat, const float *wi, const float *wo, const float *N, const int *wl, const float *uv, const int *rf,
+                       long long n, float *out) {
+    BATCH_INDEX(n)
+    out[i] = mat_eval(S.mats[mat], ld3(wi, i), ld3(wo, i), ld3(N, i), wl[i], uv[2 * i], uv[2 * i + 1], rf[i] != 0);
+}
+__global__ void k_pdf(SceneView S, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *rf, long long n, float *out) {
+    BATCH_INDEX(n)
+    out[i] = mat_pdf(S.mats[mat], ld3(wi, i), ld3(wo, i), ld3(N, i), wl[i], rf[i] != 0);
+}
+__global__ void k_fresnel(SceneView S, int mat, const float *I, const float *N, const int *wl, long long n, float *out) {
+    BATCH_INDEX(n)
+    out[i] = mat_fresnel(S.mats[mat], ld3(I, i), ld3(N, i), wl[i]);
+}
+__global__ void k_refract(SceneView S, int mat, const float *I, const float *N, const int *wl, long long n, float *out) {
+    BATCH_INDEX(n)
+    st3(out, i, mat_refract(S.mats[mat], ld3(I, i), ld3(N, i), wl[i]));
+}
+__global__ void k_reflect(const float *I, const float *N, long long n, float *out) {
+    BATCH_INDEX(n)
+    st3(out, i, mat_reflect(ld3(I, i), ld3(N, i)));
+}
+__global__ void k_msample(SceneView S, int mat, const float *N, const float *u2, long long n, float *out) {
+    BATCH_INDEX(n)
+    const Material &m = S.mats[mat];
+    f3 nn = ld3(N, i);
+    st3(out, i, mat_is_rough(m) ? ggx_sample_draws(u2[2 * i], u2[2 * i + 1], m.roughness, nn) : nn);
+}
+__global__ void k_env(SceneView S, const float *d, long long n, float *rgb) {
+    BATCH_INDEX(n)
+    st3(rgb, i, env_lookup(S, ld3(d, i)));
+}
+__global__ void k_slight(SceneView S, const float *u4, long long n, float *coords, float *normal, float *emit, float *pdf) {
+    BATCH_INDEX(n)
+    LightSample ls = sample_light(S, u4[4 * i], u4[4 * i + 1], u4[4 * i + 2], u4[4 * i + 3]);
+    st3(coords, i, ls.p); st3(normal, i, ls.n); st3(emit, i, ls.emit);
+    pdf[i] = ls.pdf;
+}
+__global__ void k_camrays(Camera cam, const int *pixels, int npix, int sample_begin, int sample_count, uint32_t k0, uint32_t k1, float *o, float *d) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)npix * sample_count) return;
+    int q = (int)(i / sample_count), k = (int)(i % sample_count);
+    int m = pixels[q];
+    Stream rs = stream_open(k0, k1, (uint32_t)m, (uint32_t)(sample_begin + k), STREAM_CAMERA, 0);
+    f3 pos, dir;
+    camera_ray(cam, m % cam.width, m / cam.width, rs, &pos, &dir);
+    st3(o, i, pos); st3(d, i, dir);
+}
+__global__ void k_uniforms(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t tag, uint32_t dim, int count, float *out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Stream rs = stream_open(k0, k1, pixel, sample, tag, dim);
+        for (int i = 0; i < count; ++i) out[i] = stream_next(rs);
+    }
+}
+__global__ void k_copy(const float4 *__restrict__ a, float4 *__restrict__ b, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct b2pt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;      // the stream all work is issued on
+    cudaStream_t own_stream = nullptr;  // created by b2pt_create
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    bool has_scene = false;
+    SceneView view{};
+    uint32_t n_prims = 0, n_materials = 0;
+    std::vector<DevBuf> scene_bufs;
+    cudaArray_t env_array = nullptr;
+    cudaTextureObject_t env_tex = 0;
+    // wave buffers
+    DevBuf wave_mem;
+    size_t wave_rays = 0;
+    int wave_ndir = 0;
+    WaveBufs wb{};
+    Counters *d_cnt = nullptr;
+    Counters *h_cnt = nullptr;  // pinned
+    DevBuf fb;                  // device accumulation buffer of b2pt_render / b2pt_render_samples
+    DevBuf pixels;
+    std::vector<DevBuf> scratch;
+};
+
+namespace {
+
+int fail(b2pt_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                                      \
+    do {                                                                                                              \
+        cudaError_t e_ = (call);                                                                                      \
+        if (e_ != cudaSuccess)                                                                                        \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? B2PT_ERR_OOM : B2PT_ERR_CUDA,                         \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                                         \
+    } while (0)
+
+int ensure(b2pt_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+    if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return 0;
+}
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+}
+int upload(b2pt_ctx *ctx, DevBuf &b, const void *src, size_t bytes) {
+    int r = ensure(ctx, b, bytes);
+    if (r) return r;
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+void free_scene(b2pt_ctx *c) {
+    for (auto &b : c->scene_bufs) release(b);
+    c->scene_bufs.clear();
+    if (c->env_tex) { cudaDestroyTextureObject(c->env_tex); c->env_tex = 0; }
+    if (c->env_array) { cudaFreeArray(c->env_array); c->env_array = nullptr; }
+    c->has_scene = false;
+}
+inline unsigned grid_for(size_t n, const b2pt_ctx *c, int per_sm) {
+    size_t blocks = (n + kBlock - 1) / kBlock;
+    size_t cap = (size_t)c->sm_count * per_sm;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)std::min(blocks, cap);
+}
+
+// Carves the wave buffers out of one allocation.
+int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
+    if (ctx->wave_rays >= rays && ctx->wave_ndir >= ndir && ctx->wave_mem.p) return 0;
+    rays = std::max(rays, ctx->wave_rays);
+    ndir = std::max(ndir, ctx->wave_ndir);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t per_queue = al(rays * 16) * 2 + al(rays * 4) * 2 + al(rays * 16 * 6);
+    size_t shadows = rays * (size_t)ndir;
+    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(shadows * 16) * 2 + al(shadows);
+    release(ctx->wave_mem);
+    ctx->wave_rays = 0;
+    int r = ensure(ctx, ctx->wave_mem, total);
+    if (r) return r;
+    char *p = (char *)ctx->wave_mem.p;
+    auto take = [&](size_t bytes) { char *q = p; p += al(bytes); return (void *)q; };
+    for (int k = 0; k < 2; ++k) {
+        Queue &q = ctx->wb.q[k];
+        q.o = (float4 *)take(rays * 16); q.d = (float4 *)take(rays * 16);
+        q.slot = (uint32_t *)take(rays * 4); q.info = (uint32_t *)take(rays * 4);
+        q.chan = (float4 *)take(rays * 16 * 6);
+        q.cap = rays;
+    }
+    ctx->wb.hit_prim = (int *)take(rays * 4);
+    ctx->wb.hit_t = (float *)take(rays * 4);
+    ctx->wb.sh_base = (uint32_t *)take(rays * 4);
+    ctx->wb.sh_o = (float4 *)take(shadows * 16);
+    ctx->wb.sh_d = (float4 *)take(shadows * 16);
+    ctx->wb.vis = (unsigned char *)take(shadows);
+    ctx->wave_rays = rays;
+    ctx->wave_ndir = ndir;
+    return 0;
+}
+
+struct RenderJob {
+    int mode;  // 0 frame, 1 listed pixels
+    const int *d_pixels;
+    int n_pixels;
+    float *d_acc;
+};
+
+int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *p, const RenderJob &job, b2pt_stats *stats) {
+    if (!ctx->has_scene) return fail(ctx, B2PT_ERR_INVALID, "no scene uploaded");
+    if (!cam || !p) return fail(ctx, B2PT_ERR_INVALID, "camera / params are NULL");
+    if (cam->width <= 0 || cam->height <= 0) return fail(ctx, B2PT_ERR_INVALID, "bad camera size");
+    if (p->spp_total <= 0 || p->sample_count < 0 || p->sample_begin < 0) return fail(ctx, B2PT_ERR_INVALID, "bad sample range");
+    CU(cudaSetDevice(ctx->device));
+    const SceneView &S = ctx->view;
+    const Camera dcam = make_camera(cam);
+    const bool count = (p->flags & B2PT_FLAG_COUNT_TRAVERSAL) != 0;
+    const int split = (p->flags & B2PT_FLAG_SPLIT_WAVELENGTHS) ? 1 : 0;
+
+    GenParams gp{};
+    gp.mode = job.mode;
+    gp.width = cam->width; gp.height = cam->height;
+    gp.tiles_x = (cam->width + 7) / 8;
+    gp.frame_slots = (unsigned)gp.tiles_x * (unsigned)((cam->height + 3) / 4) * 32u;
+    gp.sample_begin = p->sample_begin; gp.sample_count = p->sample_count;
+    gp.pixels = job.d_pixels;
+    gp.k0 = (uint32_t)p->seed; gp.k1 = (uint32_t)(p->seed >> 32);
+    gp.split = split;
+    unsigned long long total = job.mode == 0 ? (unsigned long long)gp.frame_slots * (unsigned long long)p->sample_count
+                                             : (unsigned long long)job.n_pixels * (unsigned long long)p->sample_count;
+    if (job.mode == 1 && total > 0xFFFFFFFFull / 3) return fail(ctx, B2PT_ERR_INVALID, "too many listed samples");
+
+    size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : (S.n_dir <= 8 ? (size_t)8 << 20 : (size_t)4 << 20);
+    if (wave > total) wave = (size_t)std::max<unsigned long long>(total, 1);
+    wave = (wave + kBlock - 1) / kBlock * kBlock;
+    int r = setup_wave(ctx, wave * 3, S.n_dir);
+    if (r) return r;
+
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), st));
+    CU(cudaEventRecord(ctx->ev[0], st));
+    ShadeParams sp{gp.k0, gp.k1, (float)p->spp_total, job.d_acc};
+    double extend_ms = 0, shadow_ms = 0;
+    unsigned long long launches = 0, ext_launches = 0, sh_launches = 0;
+    unsigned waves = 0;
+    Counters *dc = ctx->d_cnt;
+    for (unsigned long long first = 0; first < total; first += wave) {
+        gp.first = first;
+        gp.count = (unsigned)std::min<unsigned long long>(wave, total - first);
+        generate_kernel<<<grid_for(gp.count, ctx, 16), kBlock, 0, st>>>(dcam, gp, ctx->wb.q[0], dc);
+        swap_counts_kernel<<<1, 1, 0, st>>>(dc);
+        launches += 2;
+        waves++;
+        int cur = 0;
+        for (;;) {
+            CU(cudaMemcpyAsync(ctx->h_cnt, dc, 16, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            size_t n = ctx->h_cnt->n_cur;
+            if (n == 0) break;
+            if (n > ctx->wave_rays) return fail(ctx, B2PT_ERR_CUDA, "ray queue overflow (internal error)");
+            Queue &qa = ctx->wb.q[cur], &qb = ctx->wb.q[cur ^ 1];
+            CU(cudaEventRecord(ctx->ev[2], st));
+            if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+            else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+            CU(cudaEventRecord(ctx->ev[3], st));
+            launches++; ext_launches++;
+            if (S.enable_shadow) {
+                light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o,
+                                                                   ctx->wb.sh_d, dc, gp.k0, gp.k1);
+                CU(cudaEventRecord(ctx->ev[4], st));
+                if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, ctx->wb.vis, dc);
+                else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, ctx->wb.vis, dc);
+                CU(cudaEventRecord(ctx->ev[5], st));
+                launches += 2; sh_launches++;
+            }
+            shade_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, qb, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, dc, sp);
+            swap_counts_kernel<<<1, 1, 0, st>>>(dc);
+            launches += 2;
+            cur ^= 1;
+            CU(cudaGetLastError());
+            if (stats) {
+                // the sync at the top of the next iteration completes these events; read them lazily there
+                CU(cudaEventSynchronize(S.enable_shadow ? ctx->ev[5] : ctx->ev[3]));
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                extend_ms += ms;
+                if (S.enable_shadow) { CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); shadow_ms += ms; }
+            }
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaMemcpyAsync(ctx->h_cnt, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (stats) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        const Counters &h = *ctx->h_cnt;
+        std::memset(stats, 0, sizeof *stats);
+        stats->gpu_ms = ms; stats->extend_ms = extend_ms; stats->shadow_ms = shadow_ms;
+        stats->kernel_launches = launches; stats->extend_launches = ext_launches; stats->shadow_launches = sh_launches;
+        unsigned long long bundles = job.mode == 0 ? (unsigned long long)cam->width * cam->height * p->sample_count : total;
+        stats->bundles = bundles; stats->paths = 3 * bundles;
+        stats->rays_traced_closest = h.rays_closest; stats->rays_traced_shadow = h.rays_shadow;
+        stats->rays_reference = h.rays_reference;
+        stats->nodes_fetched = h.nodes + h.sh_nodes; stats->prims_tested = h.prims + h.sh_prims;
+        stats->extend_nodes = h.nodes; stats->extend_prims = h.prims; stats->shadow_nodes = h.sh_nodes; stats->shadow_prims = h.sh_prims;
+        stats->vertices_shaded = h.vertices;
+        stats->max_depth = h.max_depth; stats->waves = waves;
+    }
+    return B2PT_OK;
+}
+
+// scratch helpers for the batch entry points
+struct Scratch {
+    b2pt_ctx *ctx;
+    size_t next = 0;
+    int err = 0;
+    explicit Scratch(b2pt_ctx *c) : ctx(c) {}
+    void *dev(size_t bytes) {
+        if (ctx->scratch.size() <= next) ctx->scratch.resize(next + 1);
+        DevBuf &b = ctx->scratch[next++];
+        if (ensure(ctx, b, bytes)) { err = B2PT_ERR_OOM; return nullptr; }
+        return b.p;
+    }
+    template <class T>
+    T *in(const T *host, size_t count) {
+        T *d = (T *)dev(count * sizeof(T));
+        if (!d) return nullptr;
+        if (count && cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) err = B2PT_ERR_CUDA;
+        return d;
+    }
+    template <class T>
+    T *out(size_t count) { return (T *)dev(count * sizeof(T)); }
+    template <class T>
+    void back(T *host, const T *d, size_t count) {
+        if (host && count && cudaMemcpyAsync(host, d, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) err = B2PT_ERR_CUDA;
+    }
+    int finish(const char *what) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, B2PT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        if (err) return fail(ctx, err, std::string(what) + ": scratch allocation or copy failed");
+        return B2PT_OK;
+    }
+};
+inline unsigned nblocks(long long n) { return (unsigned)std::max<long long>(1, (n + 255) / 256); }
+
+#define NEED_CTX()                                                            \
+    if (!ctx) return B2PT_ERR_INVALID;                                        \
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, B2PT_ERR_CUDA, "cudaSetDevice failed");
+#define NEED_SCENE()                                                          \
+    NEED_CTX()                                                                \
+    if (!ctx->has_scene) return fail(ctx, B2PT_ERR_INVALID, "no scene uploaded");
+#define NEED_MATERIAL(m)                                                      \
+    NEED_SCENE()                                                              \
+    if ((m) < 0 || (uint32_t)(m) >= ctx->n_materials) return fail(ctx, B2PT_ERR_INVALID, "material index out of range");
+
+}  // namespace
+
+extern "C" {
+
+int b2pt_abi_version(void) { return B2PT_ABI_VERSION; }
+
+int b2pt_create(b2pt_ctx **out, int device) {
+    if (!out) return fail(nullptr, B2PT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B2PT_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(nullptr, B2PT_ERR_NO_DEVICE, "device index out of range");
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, B2PT_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, B2PT_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100: the kernels are built for sm_100a only");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, B2PT_ERR_CUDA, "cudaSetDevice failed");
+    b2pt_ctx *c = new b2pt_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&c->d_cnt, sizeof(Counters)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)) == cudaSuccess;
+    if (!ok) {
+        std::string msg = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        b2pt_destroy(c);
+        return fail(nullptr, B2PT_ERR_CUDA, msg);
+    }
+    *out = c;
+    return B2PT_OK;
+}
+
+void b2pt_destroy(b2pt_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    release(c->wave_mem); release(c->fb); release(c->pixels);
+    for (auto &b : c->scratch) release(b);
+    if (c->d_cnt) cudaFree(c->d_cnt);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *b2pt_last_error(const b2pt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b2pt_set_stream(b2pt_ctx *ctx, void *cuda_stream, int use_external) {
+    NEED_CTX()
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = use_external ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return B2PT_OK;
+}
+
+int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
+    NEED_CTX()
+    std::string err;
+    if (!validate_scene(d, err)) return fail(ctx, B2PT_ERR_INVALID, err);
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    PackedScene packed;
+    pack_scene(d, packed);
+    ctx->scene_bufs.resize(18);
+    auto up = [&](int slot, const void *src, size_t bytes) -> void * {
+        if (upload(ctx, ctx->scene_bufs[slot], src, bytes)) return nullptr;
+        return ctx->scene_bufs[slot].p;
+    };
+    SceneView v{};
+    const size_t np = d->n_prims;
+    bool ok = true;
+#define UP(field, type, slot, src, bytes) ok = ok && ((v.field = (type)up(slot, src, bytes)) != nullptr)
+    UP(nodes, const float4 *, 0, d->nodes, sizeof(b2pt_node) * (size_t)d->n_nodes);
+    UP(v0, const float4 *, 1, d->prim_v0, 16 * np);
+    UP(e1, const float4 *, 2, d->prim_e1, 16 * np);
+    UP(e2, const float4 *, 3, d->prim_e2, 16 * np);
+    UP(nrm, const float4 *, 4, d->prim_normal, 16 * np);
+    UP(v1v2, const float *, 5, d->prim_v1v2, 24 * np);
+    UP(uv, const float *, 6, d->prim_uv, 24 * np);
+    UP(prim_mat, const uint32_t *, 7, d->prim_material, 4 * np);
+    UP(prim_kind, const uint32_t *, 8, d->prim_kind, 4 * np);
+    UP(mats, const Material *, 9, packed.mats.data(), sizeof(Material) * packed.mats.size());
+    UP(light_area, const float *, 10, d->light_area, 4 * (size_t)d->n_lights);
+    UP(light_root, const uint32_t *, 11, d->light_root, 4 * (size_t)d->n_lights);
+    UP(light_mat, const uint32_t *, 12, d->light_material, 4 * (size_t)d->n_lights);
+    UP(ln_area, const float *, 13, d->light_node_area, 4 * (size_t)d->n_light_nodes);
+    UP(ln_left, const int *, 14, d->light_node_left, 4 * (size_t)d->n_light_nodes);
+    UP(ln_right, const int *, 15, d->light_node_right, 4 * (size_t)d->n_light_nodes);
+    UP(ln_prim, const int *, 16, d->light_node_prim, 4 * (size_t)d->n_light_nodes);
+#undef UP
+    if (!ok) return B2PT_ERR_CUDA;
+    v.n_lights = (int)d->n_lights;
+    v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height;
+    v.env = nullptr;
+    v.env_tex = 0;
+    if (d->use_env_map) {
+        // env map as a point-sampled float4 texture object; the bilinear weights stay the reference's (Scene.hpp:75-98)
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+        CU(cudaMallocArray(&ctx->env_array, &fmt, d->env_width, d->env_height));
+        CU(cudaMemcpy2DToArrayAsync(ctx->env_array, 0, 0, packed.env.data(), (size_t)d->env_width * 16, (size_t)d->env_width * 16, d->env_height,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = ctx->env_array;
+        cudaTextureDesc td{};
+        td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&ctx->env_tex, &rd, &td, nullptr));
+        v.env_tex = (unsigned long long)ctx->env_tex;
+        // linear copy too (kept for tools that read texels back)
+        if (upload(ctx, ctx->scene_bufs[17], packed.env.data(), packed.env.size() * 16)) return B2PT_ERR_CUDA;
+        v.env = (const float4 *)ctx->scene_bufs[17].p;
+    }
+    for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
+    v.rr_rate = d->rr_rate; v.inv_rr = d->inv_rr;
+    v.enable_shadow = d->enable_shadow; v.n_dir = d->n_dir_sample;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->view = v;
+    ctx->n_prims = d->n_prims; ctx->n_materials = d->n_materials;
+    ctx->has_scene = true;
+    return B2PT_OK;
+}
+
+int b2pt_update_scene_params(b2pt_ctx *ctx, float rr_rate, int enable_shadow, int n_dir_sample) {
+    NEED_SCENE()
+    if (rr_rate >= 0) {  // Scene::setRrRate, src/Scene.hpp:110-113
+        ctx->view.rr_rate = std::min(rr_rate, 0.99f);
+        ctx->view.inv_rr = 1 / ctx->view.rr_rate;
+    }
+    if (enable_shadow >= 0) ctx->view.enable_shadow = enable_shadow;
+    if (n_dir_sample > 0) ctx->view.n_dir = n_dir_sample;
+    return B2PT_OK;
+}
+
+int b2pt_render_device(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *p, float *out_rgb_device, b2pt_stats *stats) {
+    NEED_SCENE()
+    if (!out_rgb_device) return fail(ctx, B2PT_ERR_INVALID, "output buffer is NULL");
+    RenderJob job{0, nullptr, 0, out_rgb_device};
+    return run_render(ctx, cam, p, job, stats);
+}
+
+int b2pt_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *p, float *out_rgb_host, b2pt_stats *stats) {
+    NEED_SCENE()
+    if (!out_rgb_host || !cam) return fail(ctx, B2PT_ERR_INVALID, "output buffer / camera is NULL");
+    if (cam->width <= 0 || cam->height <= 0) return fail(ctx, B2PT_ERR_INVALID, "bad camera size");
+    size_t bytes = (size_t)cam->width * cam->height * 3 * sizeof(float);
+    int r = ensure(ctx, ctx->fb, bytes);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->fb.p, out_rgb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RenderJob job{0, nullptr, 0, (float *)ctx->fb.p};
+    r = run_render(ctx, cam, p, job, stats);
+    if (r) return r;
+    CU(cudaMemcpyAsync(out_rgb_host, ctx->fb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B2PT_OK;
+}
+
+int b2pt_render_samples(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *p, const int32_t *pixels, int32_t n_pixels,
+                        float *out_host, b2pt_stats *stats) {
+    NEED_SCENE()
+    if (!cam || !p || !pixels || !out_host || n_pixels <= 0 || p->sample_count <= 0) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < n_pixels; ++i)
+        if (pixels[i] < 0 || pixels[i] >= cam->width * cam->height) return fail(ctx, B2PT_ERR_INVALID, "pixel index out of range");
+    size_t count = (size_t)n_pixels * p->sample_count * 3;
+    int r = ensure(ctx, ctx->fb, count * sizeof(float));
+    if (r) return r;
+    r = upload(ctx, ctx->pixels, pixels, (size_t)n_pixels * sizeof(int));
+    if (r) return r;
+    CU(cudaMemsetAsync(ctx->fb.p, 0, count * sizeof(float), ctx->stream));
+    b2pt_render_params q = *p;
+    q.spp_total = 1;  // per-sample values, not divided
+    RenderJob job{1, (const int *)ctx->pixels.p, n_pixels, (float *)ctx->fb.p};
+    r = run_render(ctx, cam, &q, job, stats);
+    if (r) return r;
+    CU(cudaMemcpyAsync(out_host, ctx->fb.p, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B2PT_OK;
+}
+
+int b2pt_intersect_batch(b2pt_ctx *ctx, const float *origins, const float *dirs, int64_t n, int32_t *prim_id, double *t, b2pt_stats *stats) {
+    NEED_SCENE()
+    if (n < 0 || !origins || !dirs || !prim_id || !t) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n);
+    int *dp = s.out<int>(n);
+    double *dt = s.out<double>(n);
+    if (s.err) return s.finish("intersect_batch");
+    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), ctx->stream));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (n) {
+        if (stats) k_intersect<true><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, o, d, n, dp, dt, ctx->d_cnt);
+        else k_intersect<false><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, o, d, n, dp, dt, ctx->d_cnt);
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    s.back(prim_id, dp, n); s.back(t, dt, n);
+    if (stats) CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    int r = s.finish("intersect_batch");
+    if (r == B2PT_OK && stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        stats->gpu_ms = stats->extend_ms = ms;
+        stats->kernel_launches = stats->extend_launches = n ? 1 : 0;
+        stats->rays_traced_closest = stats->rays_reference = (uint64_t)n;
+        stats->nodes_fetched = stats->extend_nodes = ctx->h_cnt->nodes; stats->prims_tested = stats->extend_prims = ctx->h_cnt->prims;
+    }
+    return r;
+}
+
+int b2pt_shadow_batch(b2pt_ctx *ctx, const float *origins, const float *dirs, const float *dist, int64_t n, int32_t *visible, b2pt_stats *stats) {
+    NEED_SCENE()
+    if (n < 0 || !origins || !dirs || !dist || !visible) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n), *ds = s.in(dist, n);
+    int *dv = s.out<int>(n);
+    if (s.err) return s.finish("shadow_batch");
+    if (n) k_shadow<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, o, d, ds, n, dv);
+    s.back(visible, dv, n);
+    if (stats) { std::memset(stats, 0, sizeof *stats); stats->rays_traced_shadow = (uint64_t)n; stats->kernel_launches = stats->shadow_launches = n ? 1 : 0; }
+    return s.finish("shadow_batch");
+}
+
+int b2pt_tri_intersect_batch(b2pt_ctx *ctx, const float *v9, const float *origins, const float *dirs, int64_t n, int32_t *hit, double *t) {
+    NEED_CTX()
+    if (n < 0 || !v9 || !origins || !dirs || !hit || !t) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *v = s.in(v9, 9 * n), *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n);
+    int *dh = s.out<int>(n);
+    double *dt = s.out<double>(n);
+    if (s.err) return s.finish("tri_intersect_batch");
+    if (n) k_tri<<<nblocks(n), 256, 0, ctx->stream>>>(v, o, d, n, dh, dt);
+    s.back(hit, dh, n); s.back(t, dt, n);
+    return s.finish("tri_intersect_batch");
+}
+
+int b2pt_box_intersect_batch(b2pt_ctx *ctx, const float *b6, const float *origins, const float *dirs, int64_t n, int32_t *hit) {
+    NEED_CTX()
+    if (n < 0 || !b6 || !origins || !dirs || !hit) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *b = s.in(b6, 6 * n), *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n);
+    int *dh = s.out<int>(n);
+    if (s.err) return s.finish("box_intersect_batch");
+    if (n) k_box<<<nblocks(n), 256, 0, ctx->stream>>>(b, o, d, n, dh);
+    s.back(hit, dh, n);
+    return s.finish("box_intersect_batch");
+}
+
+int b2pt_sphere_intersect_batch(b2pt_ctx *ctx, const float *c4, const float *origins, const float *dirs, int64_t n, int32_t *hit, double *t,
+                                float *coords, float *normal) {
+    NEED_CTX()
+    if (n < 0 || !c4 || !origins || !dirs || !hit || !t || !coords || !normal) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *c = s.in(c4, 4 * n), *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n);
+    int *dh = s.out<int>(n);
+    double *dt = s.out<double>(n);
+    float *dc = s.out<float>(3 * n), *dn = s.out<float>(3 * n);
+    if (s.err) return s.finish("sphere_intersect_batch");
+    if (n) k_sphere<<<nblocks(n), 256, 0, ctx->stream>>>(c, o, d, n, dh, dt, dc, dn);
+    s.back(hit, dh, n); s.back(t, dt, n); s.back(coords, dc, 3 * n); s.back(normal, dn, 3 * n);
+    return s.finish("sphere_intersect_batch");
+}
+
+int b2pt_bsdf_eval_batch(b2pt_ctx *ctx, int material, const float *wi, const float *wo, const float *n, const int32_t *wavelength, const float *uv,
+                         const int32_t *is_reflect, int64_t count, float *out) {
+    NEED_MATERIAL(material)
+    if (count < 0 || !wi || !wo || !n || !wavelength || !uv || !is_reflect || !out) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(wi, 3 * count), *b = s.in(wo, 3 * count), *c = s.in(n, 3 * count), *u = s.in(uv, 2 * count);
+    const int *w = s.in(wavelength, count), *r = s.in(is_reflect, count);
+    float *d = s.out<float>(count);
+    if (s.err) return s.finish("bsdf_eval_batch");
+    if (count) k_eval<<<nblocks(count), 256, 0, ctx->stream>>>(ctx->view, material, a, b, c, w, u, r, count, d);
+    s.back(out, d, count);
+    return s.finish("bsdf_eval_batch");
+}
+
+int b2pt_bsdf_pdf_batch(b2pt_ctx *ctx, int material, const float *wi, const float *wo, const float *n, const int32_t *wavelength,
+                        const int32_t *is_reflect, int64_t count, float *out) {
+    NEED_MATERIAL(material)
+    if (count < 0 || !wi || !wo || !n || !wavelength || !is_reflect || !out) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(wi, 3 * count), *b = s.in(wo, 3 * count), *c = s.in(n, 3 * count);
+    const int *w = s.in(wavelength, count), *r = s.in(is_reflect, count);
+    float *d = s.out<float>(count);
+    if (s.err) return s.finish("bsdf_pdf_batch");
+    if (count) k_pdf<<<nblocks(count), 256, 0, ctx->stream>>>(ctx->view, material, a, b, c, w, r, count, d);
+    s.back(out, d, count);
+    return s.finish("bsdf_pdf_batch");
+}
+
+int b2pt_fresnel_batch(b2pt_ctx *ctx, int material, const float *I, const float *n, const int32_t *wavelength, int64_t count, float *out) {
+    NEED_MATERIAL(material)
+    if (count < 0 || !I || !n || !wavelength || !out) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(I, 3 * count), *c = s.in(n, 3 * count);
+    const int *w = s.in(wavelength, count);
+    float *d = s.out<float>(count);
+    if (s.err) return s.finish("fresnel_batch");
+    if (count) k_fresnel<<<nblocks(count), 256, 0, ctx->stream>>>(ctx->view, material, a, c, w, count, d);
+    s.back(out, d, count);
+    return s.finish("fresnel_batch");
+}
+
+int b2pt_refract_batch(b2pt_ctx *ctx, int material, const float *I, const float *n, const int32_t *wavelength, int64_t count, float *out3) {
+    NEED_MATERIAL(material)
+    if (count < 0 || !I || !n || !wavelength || !out3) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(I, 3 * count), *c = s.in(n, 3 * count);
+    const int *w = s.in(wavelength, count);
+    float *d = s.out<float>(3 * count);
+    if (s.err) return s.finish("refract_batch");
+    if (count) k_refract<<<nblocks(count), 256, 0, ctx->stream>>>(ctx->view, material, a, c, w, count, d);
+    s.back(out3, d, 3 * count);
+    return s.finish("refract_batch");
+}
+
+int b2pt_reflect_batch(b2pt_ctx *ctx, const float *I, const float *n, int64_t count, float *out3) {
+    NEED_CTX()
+    if (count < 0 || !I || !n || !out3) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(I, 3 * count), *c = s.in(n, 3 * count);
+    float *d = s.out<float>(3 * count);
+    if (s.err) return s.finish("reflect_batch");
+    if (count) k_reflect<<<nblocks(count), 256, 0, ctx->stream>>>(a, c, count, d);
+    s.back(out3, d, 3 * count);
+    return s.finish("reflect_batch");
+}
+
+int b2pt_material_sample_batch(b2pt_ctx *ctx, int material, const float *wo, const float *n, const float *u2, int64_t count, float *out3) {
+    NEED_MATERIAL(material)
+    (void)wo;  // Material::sample ignores the incoming direction (Material.hpp:123-130)
+    if (count < 0 || !n || !u2 || !out3) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *c = s.in(n, 3 * count), *u = s.in(u2, 2 * count);
+    float *d = s.out<float>(3 * count);
+    if (s.err) return s.finish("material_sample_batch");
+    if (count) k_msample<<<nblocks(count), 256, 0, ctx->stream>>>(ctx->view, material, c, u, count, d);
+    s.back(out3, d, 3 * count);
+    return s.finish("material_sample_batch");
+}
+
+int b2pt_env_lookup_batch(b2pt_ctx *ctx, const float *dirs, int64_t n, float *rgb) {
+    NEED_SCENE()
+    if (n < 0 || !dirs || !rgb) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(dirs, 3 * n);
+    float *d = s.out<float>(3 * n);
+    if (s.err) return s.finish("env_lookup_batch");
+    if (n) k_env<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, a, n, d);
+    s.back(rgb, d, 3 * n);
+    return s.finish("env_lookup_batch");
+}
+
+int b2pt_sample_light_batch(b2pt_ctx *ctx, const float *u4, int64_t n, float *coords, float *normal, float *emit, float *pdf) {
+    NEED_SCENE()
+    if (n < 0 || !u4 || !coords || !normal || !emit || !pdf) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    const float *a = s.in(u4, 4 * n);
+    float *dc = s.out<float>(3 * n), *dn = s.out<float>(3 * n), *de = s.out<float>(3 * n), *dp = s.out<float>(n);
+    if (s.err) return s.finish("sample_light_batch");
+    if (n) k_slight<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, a, n, dc, dn, de, dp);
+    s.back(coords, dc, 3 * n); s.back(normal, dn, 3 * n); s.back(emit, de, 3 * n); s.back(pdf, dp, n);
+    return s.finish("sample_light_batch");
+}
+
+int b2pt_camera_rays_batch(b2pt_ctx *ctx, const b2pt_camera *cam, const int32_t *pixels, int32_t n_pixels, int32_t sample_begin,
+                           int32_t sample_count, uint64_t seed, float *origins, float *dirs) {
+    NEED_CTX()
+    if (!cam || !pixels || n_pixels < 0 || sample_count < 0 || !origins || !dirs) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    long long n = (long long)n_pixels * sample_count;
+    Scratch s(ctx);
+    const int *px = s.in(pixels, n_pixels);
+    float *o = s.out<float>(3 * n), *d = s.out<float>(3 * n);
+    if (s.err) return s.finish("camera_rays_batch");
+    if (n) k_camrays<<<nblocks(n), 256, 0, ctx->stream>>>(make_camera(cam), px, n_pixels, sample_begin, sample_count, (uint32_t)seed, (uint32_t)(seed >> 32), o, d);
+    s.back(origins, o, 3 * n); s.back(dirs, d, 3 * n);
+    return s.finish("camera_rays_batch");
+}
+
+int b2pt_stream_uniforms(b2pt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t tag, uint32_t dim_begin, int32_t count, float *out) {
+    NEED_CTX()
+    if (count < 0 || !out) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    Scratch s(ctx);
+    float *d = s.out<float>(count);
+    if (s.err) return s.finish("stream_uniforms");
+    k_uniforms<<<1, 32, 0, ctx->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, tag, dim_begin, count, d);
+    s.back(out, d, count);
+    return s.finish("stream_uniforms");
+}
+
+int b2pt_measure_copy_gbs(b2pt_ctx *ctx, size_t bytes, int iters, double *gbs) {
+    NEED_CTX()
+    if (!gbs || iters <= 0 || bytes < 1024) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    bytes = bytes / 16 * 16;
+    Scratch s(ctx);
+    float4 *a = (float4 *)s.dev(bytes), *b = (float4 *)s.dev(bytes);
+    if (s.err) return s.finish("measure_copy_gbs");
+    CU(cudaMemsetAsync(a, 0, bytes, ctx->stream));
+    double best = 0;
+    for (int it = 0; it < iters + 1; ++it) {
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_copy<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, b, bytes / 16);
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        if (it > 0 && ms > 0) best = std::max(best, 2.0 * (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    *gbs = best;
+    return s.finish("measure_copy_gbs");
+}
+
+}  // extern "C"

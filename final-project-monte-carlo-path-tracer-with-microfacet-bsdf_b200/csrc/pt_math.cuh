@@ -172,6 +172,7 @@ struct SceneView {
     const int *ln_left, *ln_right, *ln_prim;
     int use_env, env_w, env_h;
     const float4 *env;      // texels as float4 (rgb, 0)
+    unsigned long long env_tex;  // the same texels as a point-sampled CUDA texture object (device only; 0 = use `env`)
     float bg[3];
     float rr_rate, inv_rr;
     int enable_shadow, n_dir;
@@ -614,8 +615,18 @@ PT_HD f3 env_lookup(const SceneView &S, f3 dir) {
     int Y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
     int Y1 = (y0 + 1) < 0 ? 0 : ((y0 + 1) > H - 1 ? H - 1 : (y0 + 1));
     float sx = x - x0, sy = y - y0;
-    f3 c00 = xyz(PT_LDG4(S.env + (size_t)Y0 * W + X0)), c10 = xyz(PT_LDG4(S.env + (size_t)Y0 * W + X1));
-    f3 c01 = xyz(PT_LDG4(S.env + (size_t)Y1 * W + X0)), c11 = xyz(PT_LDG4(S.env + (size_t)Y1 * W + X1));
+    f3 c00, c10, c01, c11;
+#if defined(__CUDA_ARCH__)
+    if (S.env_tex) {  // unnormalised coordinates + point filter: texel (X, Y) exactly; the weights below stay the reference's
+        cudaTextureObject_t tex = (cudaTextureObject_t)S.env_tex;
+        c00 = xyz(tex2D<float4>(tex, X0 + 0.5f, Y0 + 0.5f)); c10 = xyz(tex2D<float4>(tex, X1 + 0.5f, Y0 + 0.5f));
+        c01 = xyz(tex2D<float4>(tex, X0 + 0.5f, Y1 + 0.5f)); c11 = xyz(tex2D<float4>(tex, X1 + 0.5f, Y1 + 0.5f));
+    } else
+#endif
+    {
+        c00 = xyz(PT_LDG4(S.env + (size_t)Y0 * W + X0)); c10 = xyz(PT_LDG4(S.env + (size_t)Y0 * W + X1));
+        c01 = xyz(PT_LDG4(S.env + (size_t)Y1 * W + X0)); c11 = xyz(PT_LDG4(S.env + (size_t)Y1 * W + X1));
+    }
     f3 c0 = c00 * (1 - sx) + c10 * sx;
     f3 c1 = c01 * (1 - sx) + c11 * sx;
     return c0 * (1 - sy) + c1 * sy;

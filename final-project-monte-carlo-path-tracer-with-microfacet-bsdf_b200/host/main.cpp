@@ -1,0 +1,127 @@
+// host/main.cpp — ./RayTracing: the reference's program (src/main.cpp) with its hot path on the GPU.
+//
+// Same user interface as the reference: run from a directory that holds conf.json and sits beside
+// ../models (main.cpp:25-26,147), no required arguments, the same stdout lines (" - Generating BVH...",
+// "SPP: n", the progress bar, "Writing image to ...", "Rendering finished in H:M:S.ms") and the same
+// RGBA8 PNG (gamma 0.45, clamp, truncation; Renderer.cpp:93-105).  Compile with -DDEMO (make DEMO=1) for
+// the Cornell box of main.cpp:99-129, exactly like the reference's compile-time switch.
+//
+// Where the reference calls scene.buildBVH() and r.Render(scene) (main.cpp:330-333) this program calls
+// b2pt_host_scene_build -> b2pt_upload_scene -> b2pt_render: the C ABI of include/b2pt.h.
+//
+// Optional arguments (the reference ignores argv; none is needed):
+//   --demo                 DEMO scene without recompiling      --spp N, --width W, --height H   overrides
+//   --conf PATH            another conf.json                   --device D                        CUDA device
+//   --fix-ndir --fix-quality --fix-diamond --fix-output        opt-in corrections (include/b2pt_host.h)
+//   --ndir N               next-event samples per vertex       --seed S                          sample-stream key
+//   --chunk N              samples per pixel per b2pt_render call (progress granularity; default 16)
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "b2pt.h"
+#include "b2pt_host.h"
+
+static void update_progress(float progress) {  // UpdateProgress, src/global.hpp:55-70
+    int barWidth = 70;
+    std::cout << "[";
+    int pos = (int)(barWidth * progress);
+    for (int i = 0; i < barWidth; ++i) {
+        if (i < pos) std::cout << "=";
+        else if (i == pos) std::cout << ">";
+        else std::cout << " ";
+    }
+    std::cout << "] " << int(progress * 100.0) << " %\r";
+    std::cout.flush();
+}
+
+int main(int argc, char **argv) {
+#ifdef DEMO
+    bool demo = true;
+#else
+    bool demo = false;
+#endif
+    std::string conf = "conf.json", run_dir = ".";
+    int spp = 0, width = 0, height = 0, device = 0, fix = 0, ndir = 0, chunk = 16;
+    unsigned long long seed = 0x5EED0001ull;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : "0"; };
+        if (a == "--demo") demo = true;
+        else if (a == "--conf") conf = next();
+        else if (a == "--spp") spp = std::atoi(next());
+        else if (a == "--width") width = std::atoi(next());
+        else if (a == "--height") height = std::atoi(next());
+        else if (a == "--device") device = std::atoi(next());
+        else if (a == "--ndir") ndir = std::atoi(next());
+        else if (a == "--seed") seed = std::strtoull(next(), nullptr, 0);
+        else if (a == "--chunk") chunk = std::max(1, std::atoi(next()));
+        else if (a == "--fix-ndir") fix |= B2PT_HOST_FIX_DIRECT_LIGHT_SAMPLE;
+        else if (a == "--fix-quality") fix |= B2PT_HOST_FIX_MODEL_QUALITY;
+        else if (a == "--fix-diamond") fix |= B2PT_HOST_FIX_ADD_DIAMOND;
+        else if (a == "--fix-output") fix |= B2PT_HOST_FIX_OUTPUT_PATH;
+        else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    {
+        size_t s = conf.find_last_of('/');
+        if (s != std::string::npos) run_dir = conf.substr(0, s);
+    }
+    if (const char *ad = std::getenv("B2PT_ASSET_DIR")) b2pt_host_set_asset_dir(ad);
+
+    b2pt_host_scene *scene = demo ? b2pt_host_scene_demo((run_dir + "/../models").c_str(), width, height)
+                                  : b2pt_host_scene_from_conf(conf.c_str(), run_dir.c_str(), fix);
+    if (!scene) { std::fprintf(stderr, "scene assembly failed: %s\n", b2pt_host_last_error()); return 1; }
+    if (!demo && (width > 0 || height > 0)) {
+        const b2pt_camera *c = b2pt_host_scene_camera(scene);
+        b2pt_host_set_resolution(scene, width > 0 ? width : c->width, height > 0 ? height : c->height);
+    }
+    b2pt_host_set_render(scene, spp, -1.f, -1, ndir);
+
+    std::printf(" - Generating BVH...\n\n");  // Scene::buildBVH, src/Scene.cpp:15
+    if (b2pt_host_scene_build(scene) != 0) { std::fprintf(stderr, "BVH build failed: %s\n", b2pt_host_last_error()); return 1; }
+
+    b2pt_ctx *ctx = nullptr;
+    if (b2pt_create(&ctx, device) != B2PT_OK) { std::fprintf(stderr, "b2pt_create: %s\n", b2pt_last_error(nullptr)); return 1; }
+    if (b2pt_upload_scene(ctx, b2pt_host_scene_desc(scene)) != B2PT_OK) { std::fprintf(stderr, "b2pt_upload_scene: %s\n", b2pt_last_error(ctx)); return 1; }
+
+    const b2pt_camera *cam = b2pt_host_scene_camera(scene);
+    const int total_spp = b2pt_host_scene_spp(scene);
+    const std::string path = b2pt_host_scene_output_path(scene);
+    std::vector<float> framebuffer((size_t)cam->width * cam->height * 3, 0.f);
+
+    auto start = std::chrono::system_clock::now();
+    std::cout << "SPP: " << total_spp << "\n";
+    unsigned long long rays = 0;
+    double gpu_ms = 0;
+    for (int s0 = 0; s0 < total_spp; s0 += chunk) {
+        b2pt_render_params p{};
+        p.spp_total = total_spp; p.sample_begin = s0; p.sample_count = std::min(chunk, total_spp - s0);
+        p.seed = seed;
+        b2pt_stats st{};
+        if (b2pt_render(ctx, cam, &p, framebuffer.data(), &st) != B2PT_OK) { std::fprintf(stderr, "\nb2pt_render: %s\n", b2pt_last_error(ctx)); return 1; }
+        rays += st.rays_reference;
+        gpu_ms += st.gpu_ms;
+        update_progress((float)(s0 + p.sample_count) / (float)total_spp);
+    }
+    update_progress(1.f);
+    std::cout << std::endl;
+    std::cout << "Writing image to " << path << std::endl;
+    std::vector<unsigned char> raw((size_t)4 * cam->width * cam->height);
+    b2pt_host_tonemap_rgba8(framebuffer.data(), cam->width * cam->height, raw.data());
+    if (b2pt_host_write_png_rgba8(path.c_str(), raw.data(), cam->width, cam->height) != 0)
+        std::cerr << "Error when writing image : " << b2pt_host_last_error() << std::endl;
+    auto stop = std::chrono::system_clock::now();
+
+    using Milli = std::chrono::milliseconds;
+    long long ms = std::chrono::duration_cast<Milli>(stop - start).count();
+    std::cout << "Rendering finished in " << ms / 3600000 << ":" << (ms / 60000) % 60 << ":" << (ms / 1000) % 60 << "." << ms % 1000 << std::endl;
+    std::fprintf(stderr, "[b2pt] %.1f Mrays/s on the GPU (%llu rays, %.1f ms of device time)\n", gpu_ms > 0 ? rays / gpu_ms / 1e3 : 0.0, rays, gpu_ms);
+
+    b2pt_destroy(ctx);
+    b2pt_host_scene_free(scene);
+    return 0;
+}

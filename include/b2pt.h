@@ -135,7 +135,13 @@ typedef struct b2pt_render_params {
     int32_t max_wave_bundles; /* 0 = default; bundles (pixel-samples) traced per wavefront wave */
     int32_t flags;         /* B2PT_FLAG_*                                                       */
 } b2pt_render_params;
-enum { B2PT_FLAG_NONE = 0, B2PT_FLAG_COUNT_TRAVERSAL = 1 /* count nodes/prims fetched (stats build of the kernels) */ };
+enum {
+    B2PT_FLAG_NONE = 0,
+    B2PT_FLAG_COUNT_TRAVERSAL = 1,  /* count nodes/prims fetched (stats build of the traversal kernels)            */
+    B2PT_FLAG_SPLIT_WAVELENGTHS = 2 /* trace the R, G, B paths of a sample as three separate rays from the camera
+                                       on (what the reference does, Renderer.cpp:77-79) instead of sharing rays
+                                       while their geometry coincides; same result, used as a self-check          */
+};
 
 typedef struct b2pt_stats {
     double gpu_ms;                 /* CUDA-event time of the whole call's device work                   */
@@ -148,7 +154,9 @@ typedef struct b2pt_stats {
     uint64_t rays_traced_shadow;   /* traversals done by the shadow kernel                              */
     uint64_t rays_reference;       /* rays the reference algorithm needs for the same work: each traced
                                       ray counted once per wavelength path that shares it   */
-    uint64_t nodes_fetched, prims_tested; /* only with B2PT_FLAG_COUNT_TRAVERSAL                        */
+    uint64_t nodes_fetched, prims_tested; /* only with B2PT_FLAG_COUNT_TRAVERSAL (both traversal kernels)       */
+    uint64_t extend_nodes, extend_prims;  /* the same, split per kernel                                        */
+    uint64_t shadow_nodes, shadow_prims;
     uint64_t vertices_shaded;
     uint32_t max_depth, waves;
 } b2pt_stats;
@@ -162,10 +170,17 @@ int b2pt_abi_version(void);
 int b2pt_create(b2pt_ctx **out, int device);
 void b2pt_destroy(b2pt_ctx *ctx);
 const char *b2pt_last_error(const b2pt_ctx *ctx); /* ctx may be NULL: last create error */
+/* Issue all work on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream) when
+ * use_external != 0, or go back to the context's own stream.  Lets a caller bracket calls with its own
+ * CUDA events and order them against its own work (e.g. an NCCL reduce of the frame). */
+int b2pt_set_stream(b2pt_ctx *ctx, void *cuda_stream, int use_external);
 
 /* Replaces: scene.buildBVH() having run (src/main.cpp:330) — the pointer tree, the
  * per-mesh trees, Scene::objects/lightsObjects and the env map become device arrays. */
 int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *scene);
+/* Scene::setRrRate / enableShadow / setDirectLightSample (src/Scene.hpp:110-116) on the uploaded scene;
+ * rr_rate < 0, enable_shadow < 0, n_dir_sample <= 0 keep the current value. */
+int b2pt_update_scene_params(b2pt_ctx *ctx, float rr_rate, int enable_shadow, int n_dir_sample);
 
 /* ---- the hot path --------------------------------------------------------------------- */
 /* Replaces: the OpenMP pixel loop of Renderer::Render, src/Renderer.cpp:36-92.

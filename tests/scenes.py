@@ -1,0 +1,80 @@
+"""Scene fixtures shared by the CPU and GPU tests (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import os
+import tempfile
+
+import numpy as np
+
+import support as S
+
+b2pt = S.b2pt
+
+_keep = []  # temp dirs that must outlive the scenes
+
+
+def cornell(width=96, height=96, n_dir=0, rr=-1.0):
+    """DEMO scene of src/main.cpp:99-129 (BASELINE config C1 geometry)."""
+    sc = b2pt.HostScene.demo(width, height)
+    sc.set_render(0, rr, -1, n_dir)
+    return sc.build_tree(), None
+
+
+def chess(width=160, height=90, dof=True, sky=True, quality="low", n_dir=0, fix=0, king="gold_conductor", left="smooth_glass",
+          right="rough_white_conductor", spp=32):
+    """conf.json scene of src/main.cpp:137-316 with the shipped values (BASELINE configs C2/C3/C4)."""
+    tmp = tempfile.TemporaryDirectory(prefix="b2pt_chess_")
+    _keep.append(tmp)
+    run = os.path.join(tmp.name, "build")
+    os.makedirs(run)
+    os.makedirs(os.path.join(tmp.name, "models", "envoMaps"))
+    env_png = None
+    if sky:
+        env_png = S.write_sky_png(os.path.join(tmp.name, "models", "envoMaps", "sky.png"))
+        env = '"../models/envoMaps/sky.png"'
+    else:
+        env = "[0, 0, 0]"
+    conf = os.path.join(run, "conf.json")
+    with open(conf, "w") as f:
+        f.write(S.chess_conf_text(width, height, spp, dof, env, quality, king, left, right))
+    sc = b2pt.HostScene.from_conf(conf, run, fix)
+    if n_dir:
+        sc.set_render(0, -1.0, -1, n_dir)
+    return sc.build_tree(), env_png
+
+
+def two_triangle_scene():
+    """Smallest scene: an emissive quad above a rough white floor quad."""
+    sc = b2pt.HostScene.empty()
+    m = b2pt.Material(b2pt.ROUGH_CONDUCTOR, (20.0, 18.0, 15.0), 1.74, 0.1, 1.0, (0, 0, 0), 0, 0)
+    light = sc.add_material("light", m)
+    floor = np.array([[-50, 0, -50, 50, 0, -50, 50, 0, 50], [-50, 0, -50, 50, 0, 50, -50, 0, 50]], np.float32)
+    quad = np.array([[-10, 40, -10, 10, 40, 10, 10, 40, -10], [-10, 40, -10, -10, 40, 10, 10, 40, 10]], np.float32)
+    sc.add_triangles(floor, sc.find_material("rough_white_conductor"))
+    sc.add_triangles(quad, light)
+    sc.set_camera(32, 32, 60.0, (0, 30, -80), (0, 10, 0))
+    return sc.build_tree(), None
+
+
+def ray_batch(ref: "S.Ref", scene, n_pixels=600, samples=2, seed=1):
+    """Rays as the path tracer meets them: camera rays, continuation rays leaving the surfaces they hit,
+    and shadow rays towards points on the light (with their reference distances)."""
+    rng = np.random.RandomState(seed)
+    cam = scene.camera
+    px = rng.choice(cam.width * cam.height, size=min(n_pixels, cam.width * cam.height), replace=False).astype(np.int32)
+    o, d = ref.camera_rays(px, 0, samples)
+    prim, t, co, nn, uv = ref.intersect(o, d)
+    hit = prim >= 0
+    p = co[hit] + nn[hit] * np.float32(1e-4)
+    # continuation rays: random directions
+    v = rng.normal(size=p.shape).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)
+    # shadow rays: towards reference light samples
+    u4 = (np.floor(rng.rand(len(p), 4) * 16777216.0) / 16777216.0).astype(np.float32)
+    lp, ln, le, lpdf = ref.sample_light(u4)
+    w = (lp - p).astype(np.float32)
+    dist = np.sqrt((w * w).sum(1)).astype(np.float32)
+    ws = (w / dist[:, None]).astype(np.float32)
+    rays_o = np.concatenate([o, p, p]).astype(np.float32)
+    rays_d = np.concatenate([d, v, ws]).astype(np.float32)
+    return rays_o, rays_d, (p, ws, dist)

@@ -1,0 +1,194 @@
+"""CPU-only parity tests (`-m "not gpu"`): the device arithmetic of csrc/pt_math.cuh, compiled for the host
+by tests/hostcheck, against the oracle (the reference's own sources).  The `-m gpu` tests repeat these
+through the C ABI on the device; these keep the arithmetic honest on a machine without a GPU."""
+import numpy as np
+import pytest
+
+import scenes
+import support as S
+from gen import adversarial_triangle_cases, bsdf_inputs, box_cases, rel_close, sphere_cases, uniforms
+
+b2pt = S.b2pt
+pytestmark = pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref/libref_oracle.so not built")
+
+
+@pytest.fixture(scope="module", params=["cornell", "chess_sky_dof", "chess_dark"])
+def world(request):
+    if request.param == "cornell":
+        sc, env = scenes.cornell(96, 96)
+    elif request.param == "chess_sky_dof":
+        sc, env = scenes.chess(160, 90, dof=True, sky=True)
+    else:
+        sc, env = scenes.chess(160, 90, dof=False, sky=False)
+    ref = S.Ref(sc, env)
+    hc = S.HostCheck(sc)
+    yield request.param, sc, ref, hc
+    hc.close()
+    ref.close()
+    sc.close()
+
+
+def test_triangle_bit_exact():
+    v, o, d = adversarial_triangle_cases(np.random.RandomState(7), 100000)
+    hit_h, t_h = S.hc_tri(v, o, d)
+    hit_r, t_r = S.ref_tri(v, o, d)
+    assert np.array_equal(hit_h, hit_r)
+    assert 0.2 < hit_r.mean() < 0.95
+    assert np.array_equal(t_h[hit_r == 1].view(np.uint64), t_r[hit_r == 1].view(np.uint64))
+
+
+def test_box_bit_exact():
+    b6, o, d = box_cases(np.random.RandomState(8), 100000)
+    hit_r = S.ref_box(b6, o, d)
+    assert np.array_equal(S.hc_box(b6, o, d), hit_r)
+    assert 0.02 < hit_r.mean() < 0.9
+
+
+def test_sphere_bit_exact():
+    c4, o, d = sphere_cases(np.random.RandomState(9), 50000)
+    hit_h, t_h = S.hc_sphere(c4, o, d)
+    hit_r, t_r, _, _ = S.ref_sphere(c4, o, d)
+    assert np.array_equal(hit_h, hit_r)
+    assert 0.2 < hit_r.mean() < 0.99
+    assert np.array_equal(t_h[hit_r == 1].view(np.uint64), t_r[hit_r == 1].view(np.uint64))
+
+
+def test_scene_intersect_bit_exact(world):
+    name, sc, ref, hc = world
+    o, d, _ = scenes.ray_batch(ref, sc, n_pixels=1500, samples=2, seed=3)
+    prim_r, t_r, co_r, nn_r, uv_r = ref.intersect(o, d)
+    prim_h, t_h, (nodes, prims) = hc.intersect(o, d, counts=True)
+    assert np.array_equal(prim_h, prim_r), f"{name}: {(prim_h != prim_r).sum()} hit ids differ"
+    assert np.array_equal(t_h.view(np.uint64), t_r.view(np.uint64))
+    hit = prim_r >= 0
+    assert hit.mean() > 0.3
+    co_h, nn_h, uv_h = hc.surface(o, d)
+    assert np.array_equal(co_h[hit].view(np.uint32), co_r[hit].view(np.uint32))
+    assert np.array_equal(nn_h[hit].view(np.uint32), nn_r[hit].view(np.uint32))
+    assert nodes > 0 and prims > 0
+
+
+def test_textured_uv(world):
+    name, sc, ref, hc = world
+    if name == "cornell":
+        pytest.skip("no textured mesh in the Cornell scene")
+    # rays straight down onto the chessboard floor
+    rng = np.random.RandomState(5)
+    n = 4000
+    o = np.stack([rng.uniform(-600, 1100, n), np.full(n, 500.0), rng.uniform(-2400, 200, n)], 1).astype(np.float32)
+    d = np.tile(np.array([[0.01, -1.0, 0.02]], np.float32), (n, 1))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    prim_r, t_r, co_r, nn_r, uv_r = ref.intersect(o, d)
+    po, pf = sc.prim_origins()
+    floor_obj = [k for k in range(sc.n_objects) if sc.object_info(k)["kind"] == "mesh" and len(sc.object_info(k)["v9"]) == 2
+                 and sc.get_material(sc.object_info(k)["material"]).textured][0]
+    on_floor = (prim_r >= 0) & (po[np.maximum(prim_r, 0)] == floor_obj)
+    assert on_floor.mean() > 0.2
+    co_h, nn_h, uv_h = hc.surface(o, d)
+    assert np.array_equal(uv_h[on_floor].view(np.uint32), uv_r[on_floor].view(np.uint32))
+
+
+def test_shadow_decision(world):
+    name, sc, ref, hc = world
+    _, _, (p, ws, dist) = scenes.ray_batch(ref, sc, n_pixels=1500, samples=2, seed=4)
+    prim_r, t_r, *_ = ref.intersect(p, ws)
+    want = ((prim_r >= 0) & (np.abs(t_r - dist.astype(np.float64)) < np.float64(np.float32(1e-4)))).astype(np.int32)
+    got = hc.shadow(p, ws, dist)
+    assert np.array_equal(got, want), f"{name}: {(got != want).sum()} of {len(want)} visibility decisions differ"
+    assert 0.01 < want.mean() < 0.99
+
+
+def test_bsdf_parity():
+    sc, _ = scenes.two_triangle_scene()
+    ref, hc = S.Ref(sc), S.HostCheck(sc)
+    rng = np.random.RandomState(11)
+    n = 20000
+    wi, wo, nrm, wl, uv, rf = bsdf_inputs(rng, n)
+    for mat in range(len(b2pt.NAMED_MATERIALS)):
+        name = b2pt.NAMED_MATERIALS[mat]
+        assert rel_close(hc.bsdf_eval(mat, wi, wo, nrm, wl, uv, rf), ref.bsdf_eval(mat, wi, wo, nrm, wl, uv, rf), 1e-5, 1e-7).all(), (name, "eval")
+        assert rel_close(hc.bsdf_pdf(mat, wi, wo, nrm, wl, rf), ref.bsdf_pdf(mat, wi, wo, nrm, wl, rf), 1e-5, 1e-7).all(), (name, "pdf")
+        assert rel_close(hc.fresnel(mat, wi, nrm, wl), ref.fresnel(mat, wi, nrm, wl), 1e-5, 1e-7).all(), (name, "fresnel")
+        assert np.array_equal(hc.refract(mat, wi, nrm, wl).view(np.uint32), ref.refract(mat, wi, nrm, wl).view(np.uint32)), (name, "refract")
+        u2 = uniforms(rng, n, 2)
+        assert np.array_equal(hc.material_sample(mat, nrm, u2).view(np.uint32), ref.material_sample(mat, wo, nrm, u2).view(np.uint32)), (name, "sample")
+    assert np.array_equal(hc.reflect(wi, nrm).view(np.uint32), ref.reflect(0, wi, nrm).view(np.uint32))
+    # the smooth lobes and the rough lobes are both exercised (not all zeros)
+    assert (ref.bsdf_eval(b2pt.NAMED_MATERIALS.index("silver_mirror"), wi, wo, nrm, wl, uv, np.ones(n, np.int32)) > 0).mean() > 0.05
+    assert (ref.bsdf_eval(b2pt.NAMED_MATERIALS.index("rough_plastic"), wi, wo, nrm, wl, uv, rf) > 0).mean() > 0.2
+    hc.close(); ref.close(); sc.close()
+
+
+def test_textured_reflectance():
+    """Checkerboard reflectance (Material.hpp:134-151) through eval on a textured smooth conductor."""
+    sc, _ = scenes.two_triangle_scene()
+    mi = sc.find_material("silver_mirror")
+    m = sc.get_material(mi)
+    m.textured = 1
+    sc.set_material(mi, m)
+    sc.build_tree()
+    ref, hc = S.Ref(sc), S.HostCheck(sc)
+    rng = np.random.RandomState(2)
+    n = 20000
+    nrm = np.tile(np.array([[0, 1, 0]], np.float32), (n, 1))
+    wi = rng.normal(size=(n, 3)).astype(np.float32)
+    wi[:, 1] = np.abs(wi[:, 1]) + 0.1
+    wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    wo = wi * np.array([-1, 1, -1], np.float32)
+    wl = rng.randint(0, 3, n).astype(np.int32)
+    uv = (rng.rand(n, 2) * 1.4 - 0.2).astype(np.float32)
+    rf = np.ones(n, np.int32)
+    a, b = hc.bsdf_eval(mi, wi, wo, nrm, wl, uv, rf), ref.bsdf_eval(mi, wi, wo, nrm, wl, uv, rf)
+    assert rel_close(a, b, 1e-6, 1e-8).all()
+    assert len(np.unique(np.round(b, 2))) > 3
+    hc.close(); ref.close(); sc.close()
+
+
+def test_sample_light_bit_exact(world):
+    name, sc, ref, hc = world
+    u4 = uniforms(np.random.RandomState(12), 20000, 4)
+    got, want = hc.sample_light(u4), ref.sample_light(u4)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # the sqrt-warped triangle selector (BVH.cpp:132): the two triangles of the quad are NOT picked 50/50
+    assert len(np.unique(want[3])) >= 1
+
+
+def test_env_lookup(world):
+    name, sc, ref, hc = world
+    d = np.random.RandomState(13).normal(size=(20000, 3)).astype(np.float32)
+    d[:6] = [[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]]
+    g, r = hc.env(d), ref.sample_env(d)
+    assert np.array_equal(g.view(np.uint32), r.view(np.uint32))  # same libm on the host: bit-exact
+    if name == "chess_sky_dof":
+        assert r.std() > 0.01
+    else:
+        assert (r == 0).all()
+
+
+def test_camera_rays_bit_exact(world):
+    name, sc, ref, hc = world
+    cam = sc.camera
+    px = np.random.RandomState(14).choice(cam.width * cam.height, 1500, replace=False).astype(np.int32)
+    o_h, d_h = S.hc_camera_rays(cam, px, 3, 4)
+    o_r, d_r = ref.camera_rays(px, 3, 4)
+    assert np.array_equal(o_h.view(np.uint32), o_r.view(np.uint32))
+    assert np.array_equal(d_h.view(np.uint32), d_r.view(np.uint32))
+    if name == "chess_sky_dof":
+        assert len(np.unique(o_r[:, 0])) > 100  # thin lens: origins spread over the aperture
+    else:
+        assert len(np.unique(o_r[:, 0])) == 1
+
+
+def test_uniform_mapping():
+    """(word >> 8) * 2^-24 is what libstdc++'s uniform_real_distribution<float> yields for the hooked engine."""
+    u = S.hc_stream_uniforms(S.SEED, 99, 7, 0, 0, 64)
+    assert (u >= 0).all() and (u < 1).all()
+    lib = S.ref_lib()
+    for x in u[:32]:
+        assert lib.ref_uniform_from_script(float(x)) == np.float32(x)
+    # streams are functions of (seed, pixel, sample, tag, dim) only
+    assert np.array_equal(S.hc_stream_uniforms(S.SEED, 99, 7, 0, 5, 10), u[5:15])
+    assert not np.array_equal(S.hc_stream_uniforms(S.SEED, 99, 8, 0, 0, 64), u)
+    assert not np.array_equal(S.hc_stream_uniforms(S.SEED, 99, 7, 1, 0, 64), u)
+    assert abs(float(np.mean(S.hc_stream_uniforms(S.SEED, 5, 5, 0, 0, 4096))) - 0.5) < 0.02
