@@ -39,6 +39,8 @@ namespace {
 
 constexpr int kBlock = 128;
 constexpr uint32_t kNoShadow = 0xFFFFFFFFu;
+constexpr int kClasses = 5;  // 0 terminal (miss / emitter), 1 + MaterialType otherwise
+constexpr int CLASS_TERMINAL = 0;
 constexpr uint32_t INFO_DIM_MASK = 0xFFFFFu;  // bits 0-19: next draw of the path stream
 constexpr int INFO_MASK_SHIFT = 20;            // bits 20-22: wavelength paths on this ray
 constexpr uint32_t INFO_PRIMARY = 1u << 23;    // depth == 0
@@ -49,6 +51,7 @@ thread_local std::string g_create_error;
 // ---- device counters ---------------------------------------------------------------------------
 struct Counters {
     unsigned int n_cur, n_next, n_shadow, pad;
+    unsigned int n_class[8];
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
     unsigned int max_depth, pad2;
 };
@@ -69,6 +72,7 @@ struct WaveBufs {
     int *hit_prim;
     float *hit_t;
     uint32_t *sh_base;
+    uint32_t *lists;  // [kClasses][cap] ray indices by class
     float4 *sh_o;  // origin.xyz, w = dist
     float4 *sh_d;  // direction.xyz
     unsigned char *vis;
@@ -210,10 +214,12 @@ __device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int 
     else *n = normalized(*p - xyz(PT_LDG4(S.v0 + prim)));
 }
 
-// ---- light: the shadow rays of Scene::directLighting (Scene.cpp:63-73) ---------------------------------------
+// ---- light: classification + the shadow rays of Scene::directLighting (Scene.cpp:63-73) ----------------------
+// Every queued ray is filed under one of five classes — terminal (miss or emitter) or the MaterialType of
+// the surface it hit — so that the shading kernels run with warps whose lanes take the same code path.
 __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
                                                        const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ sh_o,
-                                                       float4 *__restrict__ sh_d, Counters *cnt, uint32_t k0, uint32_t k1) {
+                                                       float4 *__restrict__ sh_d, uint32_t *__restrict__ lists, Counters *cnt, uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
@@ -222,18 +228,34 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
         unsigned i = it + threadIdx.x;
         bool want = false;
+        int cls = -1;
         Ray r;
         f3 p, nn;
         uint32_t info = 0, mat = 0, kind = 0;
         float4 o4, d4;
         if (i < n) {
             int prim = hit_prim[i];
+            cls = CLASS_TERMINAL;
             if (prim >= 0) {
                 o4 = q.o[i]; d4 = q.d[i]; info = q.info[i];
                 r.o = xyz(o4); r.d = xyz(d4);
                 hit_point(S, r, prim, hit_t[i], &p, &nn, &mat, &kind);
-                want = !S.mats[mat].emissive && S.enable_shadow;
+                const Material &m = S.mats[mat];
+                if (!m.emissive) {
+                    cls = 1 + m.type;
+                    want = S.enable_shadow != 0;
+                }
             }
+        }
+        // file the ray under its class (warp-aggregated append per class)
+#pragma unroll
+        for (int c = 0; c < kClasses; ++c) {
+            unsigned b = __ballot_sync(0xffffffffu, cls == c);
+            if (!b) continue;
+            unsigned base = 0;
+            if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(&cnt->n_class[c], (unsigned)__popc(b));
+            base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+            if (cls == c) lists[(size_t)c * q.cap + base + (unsigned)__popc(b & lanemask_lt())] = i;
         }
         unsigned ballot = __ballot_sync(0xffffffffu, want);
         unsigned base = 0;
@@ -277,11 +299,80 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
     }
 }
 
-// ---- shade: one vertex of Scene::castRay (Scene.cpp:85-184) ----------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Queue qo, const unsigned *__restrict__ n_ptr,
-                                                       const int *__restrict__ hit_prim, const float *__restrict__ hit_t,
-                                                       const uint32_t *__restrict__ sh_base, const unsigned char *__restrict__ vis,
-                                                       Counters *cnt, ShadeParams sp) {
+// What a ray carries into the shading kernels.  Per-path state is held per SLOT j (the j-th wavelength path
+// on the ray, channel ch[j]) so that rays with one path each — whatever its wavelength — run in lock step.
+struct RayState {
+    Ray r;
+    uint32_t pixel, sample, slot, info, mask;
+    bool primary;
+    int nch, ch[3];
+    Phi phi[3];
+    float pend_A[3], pend_e[3], pend_f[3];
+};
+__device__ __forceinline__ void load_ray_state(const Queue &qi, unsigned i, RayState &rs) {
+    const float4 o4 = qi.o[i], d4 = qi.d[i];
+    rs.info = qi.info[i];
+    rs.pixel = __float_as_uint(o4.w); rs.sample = __float_as_uint(d4.w); rs.slot = qi.slot[i];
+    rs.mask = (rs.info >> INFO_MASK_SHIFT) & 7u;
+    rs.primary = (rs.info & INFO_PRIMARY) != 0;
+    rs.r.o = xyz(o4); rs.r.d = xyz(d4);
+    rs.nch = __popc(rs.mask);
+    uint32_t mm = rs.mask;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        rs.ch[j] = mm ? __ffs(mm) - 1 : 0;
+        mm &= mm - 1;
+        rs.phi[j].M = 1.f; rs.phi[j].K = 0.f; rs.phi[j].L = -INFINITY; rs.phi[j].U = INFINITY;
+        rs.pend_A[j] = rs.pend_e[j] = rs.pend_f[j] = 0.f;
+        if (!rs.primary && j < rs.nch) {
+            float4 a = qi.chan[(size_t)(rs.ch[j] * 2) * qi.cap + i], b = qi.chan[(size_t)(rs.ch[j] * 2 + 1) * qi.cap + i];
+            rs.phi[j].M = a.x; rs.phi[j].K = a.y; rs.phi[j].L = a.z; rs.phi[j].U = a.w;
+            rs.pend_A[j] = b.x; rs.pend_e[j] = b.y; rs.pend_f[j] = b.z;
+        }
+    }
+}
+
+// ---- terminal: rays that missed or hit an emitter (Scene.cpp:88-95,102-107,145-148,172-175) ---------------------------
+__global__ void __launch_bounds__(kBlock) terminal_kernel(SceneView S, Queue qi, const uint32_t *__restrict__ list, const unsigned *__restrict__ n_ptr,
+                                                          const int *__restrict__ hit_prim, const float *__restrict__ hit_t, ShadeParams sp) {
+    const unsigned n = *n_ptr;
+    for (unsigned li = blockIdx.x * kBlock + threadIdx.x; li < n; li += gridDim.x * kBlock) {
+        const unsigned i = list[li];
+        RayState rs;
+        load_ray_state(qi, i, rs);
+        const int prim = hit_prim[i];
+        float *acc = sp.acc + 3 * (size_t)rs.slot;
+        f3 env = mk3(0, 0, 0), emis = mk3(0, 0, 0);
+        float cosn = 0.f;
+        if (!rs.primary || prim < 0) env = env_lookup(S, rs.r.d);
+        else {  // depth 0 and an emitter: clamp(0, 1, Le * |wo.n|)
+            f3 p, nn;
+            uint32_t mat, kind;
+            hit_point(S, rs.r, prim, hit_t[i], &p, &nn, &mat, &kind);
+            const Material &m = S.mats[mat];
+            emis = mk3(m.emission[0], m.emission[1], m.emission[2]);
+            cosn = fabsf(dot(-rs.r.d, nn));
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j >= rs.nch) continue;
+            const int c = rs.ch[j];
+            float v;
+            if (rs.primary) v = (prim < 0) ? comp(env, c) : clamp_ref(0.f, 1.f, comp(emis, c) * cosn);
+            else v = phi_apply(rs.phi[j], rs.pend_A[j] + clamp_ref(0.f, 5.f, (comp(env, c) * rs.pend_e[j]) * S.inv_rr));
+            atomicAdd(acc + c, v / sp.div);
+        }
+    }
+}
+
+// ---- shade: one vertex of Scene::castRay (Scene.cpp:109-183) on a surface of material type TYPE -------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Queue qo, const uint32_t *__restrict__ list,
+                                                       const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
+                                                       const float *__restrict__ hit_t, const uint32_t *__restrict__ sh_base,
+                                                       const unsigned char *__restrict__ vis, Counters *cnt, ShadeParams sp) {
+    constexpr bool ROUGH = (TYPE == MAT_ROUGH_CONDUCTOR || TYPE == MAT_ROUGH_DIELECTRIC);
+    constexpr bool CONDUCTOR = (TYPE == MAT_SMOOTH_CONDUCTOR || TYPE == MAT_ROUGH_CONDUCTOR);
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
@@ -289,155 +380,119 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Qu
     unsigned long long verts = 0;
     unsigned maxd = 0;
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
-        const unsigned i = it + threadIdx.x;
+        const unsigned li = it + threadIdx.x;
         int n_emit = 0;
-        // continuation rays this lane emits (at most one per wavelength path)
         f3 e_o[3], e_d[3];
         uint32_t e_mask[3] = {0, 0, 0};
-        Phi phi[3];
         float lvl_A[3], lvl_e[3], lvl_f[3];
-        uint32_t pixel = 0, sample = 0, slot = 0, new_info = 0;
+        uint32_t new_info = 0;
+        RayState rs;
+        rs.nch = 0; rs.pixel = rs.sample = rs.slot = 0;
 
-        if (i < n) {
-            const float4 o4 = qi.o[i], d4 = qi.d[i];
-            const uint32_t info = qi.info[i];
-            pixel = __float_as_uint(o4.w); sample = __float_as_uint(d4.w); slot = qi.slot[i];
-            const uint32_t mask = (info >> INFO_MASK_SHIFT) & 7u;
-            const bool primary = (info & INFO_PRIMARY) != 0;
-            const uint32_t depth = info >> INFO_DEPTH_SHIFT;
-            Ray r;
-            r.o = xyz(o4); r.d = xyz(d4);
-            const int prim = hit_prim[i];
-            float *acc = sp.acc + 3 * (size_t)slot;
-
-            // state carried by the ray: the path map and the level whose probe ray this is
-            float pend_A[3] = {0, 0, 0}, pend_e[3] = {0, 0, 0}, pend_f[3] = {0, 0, 0};
+        if (li < n) {
+            const unsigned i = list[li];
+            load_ray_state(qi, i, rs);
+            const uint32_t depth = rs.info >> INFO_DEPTH_SHIFT;
+            float *acc = sp.acc + 3 * (size_t)rs.slot;
+            Hit h;
+            h.prim = hit_prim[i]; h.t = (double)hit_t[i];
+            const Surface s = surface_at(S, rs.r, h);
+            Material m = S.mats[s.mat];
+            m.type = TYPE;  // known at compile time: folds the type switches of Material.hpp
+            const f3 wo = -rs.r.d;
+            verts += (unsigned)rs.nch;
+            if (depth > maxd) maxd = depth;
+            if (!rs.primary) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                phi[c].M = 1.f; phi[c].K = 0.f; phi[c].L = -INFINITY; phi[c].U = INFINITY;
-                if (!primary && (mask >> c & 1u)) {
-                    float4 a = qi.chan[(size_t)(c * 2) * qi.cap + i], b = qi.chan[(size_t)(c * 2 + 1) * qi.cap + i];
-                    phi[c].M = a.x; phi[c].K = a.y; phi[c].L = a.z; phi[c].U = a.w;
-                    pend_A[c] = b.x; pend_e[c] = b.y; pend_f[c] = b.z;
-                }
+                for (int j = 0; j < 3; ++j)
+                    if (j < rs.nch) rs.phi[j] = phi_compose(rs.phi[j], rs.pend_A[j], rs.pend_f[j]);
             }
-
-            Material m;
-            Surface s;
-            bool terminal = prim < 0;
-            if (!terminal) {
-                Hit h; h.prim = prim; h.t = (double)hit_t[i];
-                s = surface_at(S, r, h);
-                m = S.mats[s.mat];
-                terminal = m.emissive != 0;
+            const f3 nrm = s.n;
+            Stream st = stream_open(sp.k0, sp.k1, rs.pixel, rs.sample, STREAM_PATH, rs.info & INFO_DIM_MASK);
+            f3 mfn = nrm;  // Material::sample, Material.hpp:268-281
+            if (ROUGH) {
+                float a = stream_next(st), b = stream_next(st);
+                mfn = ggx_sample_draws(a, b, m.roughness, nrm);
             }
-            const f3 wo = -r.d;
-            if (terminal) {
-                // miss -> env (Scene.cpp:88-95); depth 0 emitter -> clamp(0,1,Le|wo.n|) (Scene.cpp:102-107);
-                // a probe ray that misses or hits an emitter -> env term of Scene.cpp:145-148,172-175.
-                f3 env = mk3(0, 0, 0);
-                if (!primary || prim < 0) env = env_lookup(S, r.d);
+            float kr[3], ldir[3] = {0, 0, 0};
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (!(mask >> c & 1u)) continue;
-                    float v;
-                    if (primary) v = (prim < 0) ? comp(env, c) : clamp_ref(0.f, 1.f, m.emission[c] * fabsf(dot(wo, s.n)));
-                    else v = phi_apply(phi[c], pend_A[c] + clamp_ref(0.f, 5.f, (comp(env, c) * pend_e[c]) * S.inv_rr));
-                    atomicAdd(acc + c, v / sp.div);
-                }
+            for (int j = 0; j < 3; ++j) kr[j] = (CONDUCTOR || j >= rs.nch) ? 1.f : mat_fresnel(m, rs.r.d, mfn, rs.ch[j]);
+            // direct light, Scene.cpp:56-82,114-119
+            const bool inner = dot(wo, nrm) < 0;
+            const f3 pn = s.p + nrm * kEps;
+            const uint32_t sb = sh_base[i];
+            for (int k = 0; k < ndir; ++k) {
+                float u0 = stream_next(st), u1 = stream_next(st), u2 = stream_next(st), u3 = stream_next(st);
+                bool lit = !S.enable_shadow || (sb != kNoShadow && vis[sb + k]);
+                if (!lit) continue;
+                NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < rs.nch) ldir[j] += nee_term(m, g, wo, nrm, rs.ch[j], s.u, s.v, !inner, ndir);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ldir[j] = inner ? (float)((1. - (double)kr[j]) * (double)ldir[j]) : kr[j] * ldir[j];
+
+            const float rr = stream_next(st), rd = stream_next(st);
+            const uint32_t new_dim = st.dim;
+            if (rr >= S.rr_rate) {  // Scene.cpp:129-131,156-158: the raw l_dir is returned
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < rs.nch) atomicAdd(acc + rs.ch[j], phi_apply(rs.phi[j], ldir[j]) / sp.div);
             } else {
-                verts += (unsigned)__popc(mask);
-                if (depth > maxd) maxd = depth;
-                if (!primary) {
+                const bool back = dot(wo, mfn) < 0;
+                const float cosn = fabsf(dot(wo, nrm));
+                const f3 p_refl = back ? s.p - nrm * kEps : s.p + nrm * kEps;  // Scene.cpp:124-128
+                const f3 p_refr = back ? s.p + nrm * kEps : s.p - nrm * kEps;  // Scene.cpp:151-155
+                const f3 wi_refl = mat_reflect(wo, mfn);
+                f3 wi[3];
+                bool refl[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (mask >> c & 1u) phi[c] = phi_compose(phi[c], pend_A[c], pend_f[c]);
+                for (int j = 0; j < 3; ++j) {
+                    refl[j] = CONDUCTOR || rd < kr[j];
+                    wi[j] = wi_refl;
+                    if (!CONDUCTOR && j < rs.nch && !refl[j]) wi[j] = mat_refract(m, rs.r.d, mfn, rs.ch[j]);
                 }
-                const f3 nrm = s.n;
-                const bool rough = mat_is_rough(m);
-                Stream rs = stream_open(sp.k0, sp.k1, pixel, sample, STREAM_PATH, info & INFO_DIM_MASK);
-                f3 mfn = nrm;  // Material::sample, Material.hpp:268-281
-                if (rough) {
-                    float a = stream_next(rs), b = stream_next(rs);
-                    mfn = ggx_sample_draws(a, b, m.roughness, nrm);
-                }
-                float kr[3], ldir[3] = {0, 0, 0};
-#pragma unroll
-                for (int c = 0; c < 3; ++c) kr[c] = (mask >> c & 1u) ? mat_fresnel(m, r.d, mfn, c) : 0.f;
-                // direct light, Scene.cpp:56-82,114-119
-                const bool inner = dot(wo, nrm) < 0;
-                const f3 pn = s.p + nrm * kEps;
-                const uint32_t sb = sh_base[i];
-                for (int k = 0; k < ndir; ++k) {
-                    float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
-                    bool lit = !S.enable_shadow || (sb != kNoShadow && vis[sb + k]);
-                    if (!lit) continue;
-                    NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (mask >> c & 1u) ldir[c] += nee_term(m, g, wo, nrm, c, s.u, s.v, !inner, ndir);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    ldir[c] = inner ? (float)((1. - (double)kr[c]) * (double)ldir[c]) : kr[c] * ldir[c];
-
-                const float rr = stream_next(rs), rd = stream_next(rs);
-                const uint32_t new_dim = rs.dim;
-                if (rr >= S.rr_rate) {  // Scene.cpp:129-131,156-158: the raw l_dir is returned
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (mask >> c & 1u) atomicAdd(acc + c, phi_apply(phi[c], ldir[c]) / sp.div);
+                if (CONDUCTOR) {  // kr == 1: every path reflects, the ray stays whole
+                    e_o[0] = p_refl; e_d[0] = wi_refl; e_mask[0] = rs.mask; n_emit = 1;
                 } else {
-                    const bool back = dot(wo, mfn) < 0;
-                    const bool dirac = !rough;
-                    const float cosn = fabsf(dot(wo, nrm));
-                    const f3 p_refl = back ? s.p - nrm * kEps : s.p + nrm * kEps;  // Scene.cpp:124-128
-                    const f3 p_refr = back ? s.p + nrm * kEps : s.p - nrm * kEps;  // Scene.cpp:151-155
-                    const f3 wi_refl = mat_reflect(wo, mfn);
-                    f3 wi[3];
-                    bool refl[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        refl[c] = rd < kr[c];
-                        wi[c] = wi_refl;
-                        if ((mask >> c & 1u) && !refl[c]) wi[c] = mat_refract(m, r.d, mfn, c);
-                    }
                     uint32_t done = 0;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (!(mask >> c & 1u) || (done >> c & 1u)) continue;
-                        uint32_t gm = 1u << c;
+                    for (int j = 0; j < 3; ++j) {
+                        if (j >= rs.nch || (done >> j & 1u)) continue;
+                        uint32_t gs = 1u << j, gm = 1u << rs.ch[j];
 #pragma unroll
-                        for (int c2 = c + 1; c2 < 3; ++c2) {
-                            if (!(mask >> c2 & 1u) || (done >> c2 & 1u) || refl[c2] != refl[c]) continue;
-                            if (refl[c] || (f2u(wi[c2].x) == f2u(wi[c].x) && f2u(wi[c2].y) == f2u(wi[c].y) && f2u(wi[c2].z) == f2u(wi[c].z)))
-                                gm |= 1u << c2;
+                        for (int j2 = j + 1; j2 < 3; ++j2) {
+                            if (j2 >= rs.nch || (done >> j2 & 1u) || refl[j2] != refl[j]) continue;
+                            if (refl[j] || (f2u(wi[j2].x) == f2u(wi[j].x) && f2u(wi[j2].y) == f2u(wi[j].y) && f2u(wi[j2].z) == f2u(wi[j].z))) {
+                                gs |= 1u << j2; gm |= 1u << rs.ch[j2];
+                            }
                         }
-                        done |= gm;
-                        e_o[n_emit] = refl[c] ? p_refl : p_refr;
-                        e_d[n_emit] = wi[c];
+                        done |= gs;
+                        e_o[n_emit] = refl[j] ? p_refl : p_refr;
+                        e_d[n_emit] = wi[j];
                         e_mask[n_emit] = gm;
                         n_emit++;
                     }
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (!(mask >> c & 1u)) continue;
-                        float ev = mat_eval(m, wi[c], wo, nrm, c, s.u, s.v, refl[c]);
-                        float f;
-                        if (dirac) f = ev * S.inv_rr;
-                        else f = ((ev * cosn) / mat_pdf(m, wi[c], wo, nrm, c, refl[c])) * S.inv_rr;
-                        lvl_A[c] = clamp_ref(0.f, 15.f, ldir[c]);
-                        lvl_e[c] = ev;
-                        lvl_f[c] = f;
-                    }
-                    uint32_t nd = depth < 255u ? depth + 1u : 255u;
-                    new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT);
                 }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (j >= rs.nch) continue;
+                    float ev = mat_eval(m, wi[j], wo, nrm, rs.ch[j], s.u, s.v, refl[j]);
+                    float f;
+                    if (!ROUGH) f = ev * S.inv_rr;  // isDirac
+                    else f = ((ev * cosn) / mat_pdf(m, wi[j], wo, nrm, rs.ch[j], refl[j])) * S.inv_rr;
+                    lvl_A[j] = clamp_ref(0.f, 15.f, ldir[j]);
+                    lvl_e[j] = ev;
+                    lvl_f[j] = f;
+                }
+                uint32_t nd = depth < 255u ? depth + 1u : 255u;
+                new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT);
             }
         }
         // append the continuation rays: warp scan over "emits >= 1 / 2 / 3 rays"
-        unsigned b1 = __ballot_sync(0xffffffffu, n_emit >= 1), b2 = __ballot_sync(0xffffffffu, n_emit >= 2),
-                 b3 = __ballot_sync(0xffffffffu, n_emit >= 3);
+        unsigned b1 = __ballot_sync(0xffffffffu, n_emit >= 1);
+        unsigned b2 = CONDUCTOR ? 0u : __ballot_sync(0xffffffffu, n_emit >= 2), b3 = CONDUCTOR ? 0u : __ballot_sync(0xffffffffu, n_emit >= 3);
         unsigned total = (unsigned)(__popc(b1) + __popc(b2) + __popc(b3));
         unsigned base = 0;
         if (lane == 0 && total) base = atomicAdd(&cnt->n_next, total);
@@ -446,15 +501,15 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Qu
             unsigned lt = lanemask_lt();
             unsigned p = base + (unsigned)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt));
             for (int k = 0; k < n_emit; ++k) {
-                qo.o[p + k] = make_float4(e_o[k].x, e_o[k].y, e_o[k].z, __uint_as_float(pixel));
-                qo.d[p + k] = make_float4(e_d[k].x, e_d[k].y, e_d[k].z, __uint_as_float(sample));
-                qo.slot[p + k] = slot;
+                qo.o[p + k] = make_float4(e_o[k].x, e_o[k].y, e_o[k].z, __uint_as_float(rs.pixel));
+                qo.d[p + k] = make_float4(e_d[k].x, e_d[k].y, e_d[k].z, __uint_as_float(rs.sample));
+                qo.slot[p + k] = rs.slot;
                 qo.info[p + k] = new_info | (e_mask[k] << INFO_MASK_SHIFT);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (!(e_mask[k] >> c & 1u)) continue;
-                    qo.chan[(size_t)(c * 2) * qo.cap + p + k] = make_float4(phi[c].M, phi[c].K, phi[c].L, phi[c].U);
-                    qo.chan[(size_t)(c * 2 + 1) * qo.cap + p + k] = make_float4(lvl_A[c], lvl_e[c], lvl_f[c], 0.f);
+                for (int j = 0; j < 3; ++j) {
+                    if (j >= rs.nch || !(e_mask[k] >> rs.ch[j] & 1u)) continue;
+                    qo.chan[(size_t)(rs.ch[j] * 2) * qo.cap + p + k] = make_float4(rs.phi[j].M, rs.phi[j].K, rs.phi[j].L, rs.phi[j].U);
+                    qo.chan[(size_t)(rs.ch[j] * 2 + 1) * qo.cap + p + k] = make_float4(lvl_A[j], lvl_e[j], lvl_f[j], 0.f);
                 }
             }
         }
@@ -473,6 +528,7 @@ __global__ void swap_counts_kernel(Counters *cnt) {
     cnt->n_cur = cnt->n_next;
     cnt->n_next = 0;
     cnt->n_shadow = 0;
+    for (int c = 0; c < kClasses; ++c) cnt->n_class[c] = 0;
 }
 
 // ---- batch kernels for the parity entry points ---------------------------------------------------------------
@@ -672,7 +728,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t per_queue = al(rays * 16) * 2 + al(rays * 4) * 2 + al(rays * 16 * 6);
     size_t shadows = rays * (size_t)ndir;
-    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(shadows * 16) * 2 + al(shadows);
+    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows);
     release(ctx->wave_mem);
     ctx->wave_rays = 0;
     int r = ensure(ctx, ctx->wave_mem, total);
@@ -689,6 +745,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     ctx->wb.hit_prim = (int *)take(rays * 4);
     ctx->wb.hit_t = (float *)take(rays * 4);
     ctx->wb.sh_base = (uint32_t *)take(rays * 4);
+    ctx->wb.lists = (uint32_t *)take(rays * 4 * kClasses);
     ctx->wb.sh_o = (float4 *)take(shadows * 16);
     ctx->wb.sh_d = (float4 *)take(shadows * 16);
     ctx->wb.vis = (unsigned char *)take(shadows);
@@ -762,18 +819,27 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
             CU(cudaEventRecord(ctx->ev[3], st));
             launches++; ext_launches++;
+            light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o,
+                                                               ctx->wb.sh_d, ctx->wb.lists, dc, gp.k0, gp.k1);
+            launches++;
             if (S.enable_shadow) {
-                light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o,
-                                                                   ctx->wb.sh_d, dc, gp.k0, gp.k1);
                 CU(cudaEventRecord(ctx->ev[4], st));
                 if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, ctx->wb.vis, dc);
                 else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, ctx->wb.vis, dc);
                 CU(cudaEventRecord(ctx->ev[5], st));
-                launches += 2; sh_launches++;
+                launches++; sh_launches++;
             }
-            shade_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, qb, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, dc, sp);
-            swap_counts_kernel<<<1, 1, 0, st>>>(dc);
-            launches += 2;
+            {
+                const unsigned g = grid_for(n, ctx, 16);
+                const uint32_t *L = ctx->wb.lists;
+                const size_t cap = qa.cap;
+                terminal_kernel<<<g, kBlock, 0, st>>>(S, qa, L, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
+#define SHADE(T) shade_kernel<T><<<g, kBlock, 0, st>>>(S, qa, qb, L + (size_t)(1 + T) * cap, &dc->n_class[1 + T], ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, dc, sp)
+                SHADE(MAT_SMOOTH_CONDUCTOR); SHADE(MAT_ROUGH_CONDUCTOR); SHADE(MAT_SMOOTH_DIELECTRIC); SHADE(MAT_ROUGH_DIELECTRIC);
+#undef SHADE
+                swap_counts_kernel<<<1, 1, 0, st>>>(dc);
+                launches += 6;
+            }
             cur ^= 1;
             CU(cudaGetLastError());
             if (stats) {
