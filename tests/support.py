@@ -473,3 +473,98 @@ def chess_conf_text(w=1920, h=1080, spp=2048, dof=True, env='"../models/envoMaps
                     left="smooth_glass", right="rough_white_conductor"):
     soldiers = ", ".join(['"%s"' % left] * 7 + ['"%s"' % right] * 7)
     return CHESS_CONF % dict(w=w, h=h, spp=spp, dof="true" if dof else "false", env=env, quality=quality, king=king, soldiers=soldiers)
+
+
+# ---- oracle/pt_oracle.c: the plain-C restatement ----------------------------------------------------------------
+PTO_LIB = os.path.join(ROOT, "oracle", "libpt_oracle.so")
+_pto = None
+
+
+def pto_lib():
+    global _pto
+    if _pto is None:
+        if not os.path.exists(PTO_LIB):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "libpt_oracle.so"], check=True, capture_output=True)
+        L = C.CDLL(PTO_LIB)
+        L.pto_scene_new.restype = C.c_void_p
+        L.pto_scene_new.argtypes = [C.POINTER(b2pt.SceneDesc)]
+        L.pto_scene_free.argtypes = [C.c_void_p]
+        L.pto_describe.restype = C.c_char_p
+        _pto = L
+    return _pto
+
+
+class Restated:
+    """oracle/pt_oracle.c over a flattened scene (recursive castRay, exhaustive BVH walk)."""
+
+    def __init__(self, scene: "b2pt.HostScene"):
+        self.L = pto_lib()
+        self.scene = scene
+        self.h = C.c_void_p(self.L.pto_scene_new(C.byref(scene.desc)))
+
+    def close(self):
+        if self.h:
+            self.L.pto_scene_free(self.h)
+            self.h = None
+
+    def intersect(self, o, d):
+        o, d = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
+        prim = np.zeros(len(o), np.int32)
+        t = np.zeros(len(o), np.float64)
+        self.L.pto_intersect(self.h, fp(o), fp(d), C.c_long(len(o)), ip(prim), t.ctypes.data_as(c_double_p))
+        return prim, t
+
+    def bsdf_eval(self, mat, wi, wo, n, wl, uv, rf):
+        wi, wo, n, uv, wl, rf = f32(wi), f32(wo), f32(n), f32(uv), i32(wl), i32(rf)
+        out = np.zeros(len(wl), np.float32)
+        self.L.pto_bsdf_eval(self.h, mat, fp(wi), fp(wo), fp(n), ip(wl), fp(uv), ip(rf), C.c_long(len(wl)), fp(out))
+        return out
+
+    def bsdf_pdf(self, mat, wi, wo, n, wl, rf):
+        wi, wo, n, wl, rf = f32(wi), f32(wo), f32(n), i32(wl), i32(rf)
+        out = np.zeros(len(wl), np.float32)
+        self.L.pto_bsdf_pdf(self.h, mat, fp(wi), fp(wo), fp(n), ip(wl), ip(rf), C.c_long(len(wl)), fp(out))
+        return out
+
+    def sample_env(self, d):
+        d = f32(d).reshape(-1, 3)
+        out = np.zeros((len(d), 3), np.float32)
+        self.L.pto_sample_env(self.h, fp(d), C.c_long(len(d)), fp(out))
+        return out
+
+    def sample_light(self, u4):
+        u = f32(u4).reshape(-1, 4)
+        co, nn, em = (np.zeros((len(u), 3), np.float32) for _ in range(3))
+        pdf = np.zeros(len(u), np.float32)
+        self.L.pto_sample_light(self.h, fp(u), C.c_long(len(u)), fp(co), fp(nn), fp(em), fp(pdf))
+        return co, nn, em, pdf
+
+    def camera_rays(self, pixels, sample_begin, sample_count, seed=SEED):
+        px = i32(pixels)
+        n = len(px) * sample_count
+        o, d = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        cam = self.scene.camera
+        self.L.pto_camera_rays(C.byref(cam), ip(px), len(px), sample_begin, sample_count, C.c_uint64(seed), fp(o), fp(d))
+        return o, d
+
+    def render_samples(self, pixels, sample_begin, sample_count, seed=SEED):
+        px = i32(pixels)
+        out = np.zeros((len(px), sample_count, 3), np.float32)
+        cam = self.scene.camera
+        self.L.pto_render_samples(self.h, C.byref(cam), ip(px), len(px), sample_begin, sample_count, C.c_uint64(seed), fp(out))
+        return out
+
+    def render_frame(self, sample_begin, sample_count, spp_total, seed=SEED, fb=None):
+        cam = self.scene.camera
+        if fb is None:
+            fb = np.zeros((cam.height, cam.width, 3), np.float32)
+        self.L.pto_render_frame(self.h, C.byref(cam), sample_begin, sample_count, spp_total, C.c_uint64(seed), fp(fb))
+        return fb
+
+
+def pto_tri(v9, o, d):
+    v, o, d = f32(v9).reshape(-1, 9), f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
+    hit = np.zeros(len(o), np.int32)
+    t = np.zeros(len(o), np.float64)
+    pto_lib().pto_tri_intersect(fp(v), fp(o), fp(d), C.c_long(len(o)), ip(hit), t.ctypes.data_as(c_double_p))
+    return hit, t
