@@ -52,6 +52,8 @@ thread_local std::string g_create_error;
 struct Counters {
     unsigned int n_cur, n_next, n_shadow, pad;
     unsigned int n_class[8];
+    unsigned int fetch_extend, fetch_shadow;  // dynamic-fetch cursors of the traversal kernels
+    unsigned int pad1[2];
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
     unsigned int max_depth, pad2;
 };
@@ -181,25 +183,62 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
 }
 
 // ---- extend: Scene::intersect for every queued ray ---------------------------------------------------------
+// Persistent warps with dynamic ray fetch: the walks of a warp's 32 rays are stepped together; when the
+// number of lanes still walking falls to kRefillBelow the idle lanes take new rays from the queue (one
+// warp-aggregated atomic), so a few long walks do not leave the warp mostly empty.
+constexpr int kRefillBelow = 20;
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
                                                         const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
-                                                        int *__restrict__ hit_prim, float *__restrict__ hit_t, Counters *cnt) {
+                                                        unsigned *__restrict__ next, int *__restrict__ hit_prim, float *__restrict__ hit_t,
+                                                        Counters *cnt) {
     const unsigned n = *n_ptr;
-    unsigned long long nodes = 0, prims = 0, refs = 0;
-    for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-        float4 o = qo[i], d = qd[i];
-        Ray r = make_ray(xyz(o), xyz(d));
-        TravStats st{0, 0};
-        Hit h = closest_hit<COUNT>(S, r, &st);
-        hit_prim[i] = h.prim;
-        hit_t[i] = (float)h.t;  // Ray::operator()(double t) converts t to float before use
-        if (COUNT) { nodes += st.nodes; prims += st.prims; }
-        refs += (unsigned)__popc((qinfo[i] >> INFO_MASK_SHIFT) & 7u);
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long refs = 0;
+    TravStats st{0, 0};
+    bool has = false, exhausted = false;
+    unsigned idx = 0;
+    Ray r;
+    Trav T;
+    r.o = r.d = r.inv = mk3(0, 0, 0);
+    trav_begin(T);
+    for (;;) {
+        if (!exhausted) {
+            unsigned need = __ballot_sync(0xffffffffu, !has);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                unsigned base = 0;
+                if ((int)lane == leader) base = atomicAdd(next, (unsigned)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!has) {
+                    idx = base + (unsigned)__popc(need & lanemask_lt());
+                    if (idx < n) {
+                        float4 o = qo[idx], d = qd[idx];
+                        r = make_ray(xyz(o), xyz(d));
+                        trav_begin(T);
+                        has = true;
+                        refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
+                    }
+                }
+                exhausted = base + (unsigned)__popc(need) >= n;
+            }
+        }
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!act) break;
+        do {
+            if (has && !trav_step<COUNT>(S, r, T, &st)) {
+                hit_prim[idx] = T.h.prim;
+                hit_t[idx] = (float)T.h.t;  // Ray::operator()(double t) converts t to float before use
+                has = false;
+            }
+            act = __ballot_sync(0xffffffffu, has);
+        } while (act && (exhausted || __popc(act) > kRefillBelow));
     }
     refs = warp_sum(refs);
+    unsigned long long nodes = st.nodes, prims = st.prims;
     if (COUNT) { nodes = warp_sum(nodes); prims = warp_sum(prims); }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (refs) atomicAdd(&cnt->rays_reference, refs);
         if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
     }
@@ -280,22 +319,55 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
     if (lane == 0 && refs) atomicAdd(&cnt->rays_reference, refs);
 }
 
-// ---- shadow: the visibility decision of Scene.cpp:72-75 -----------------------------------------------------------
+// ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
-                                                        const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis, Counters *cnt) {
+                                                        const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
+                                                        unsigned char *__restrict__ vis, Counters *cnt) {
     const unsigned n = *n_ptr;
-    unsigned long long nodes = 0, prims = 0;
-    for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-        float4 o = sh_o[i], d = sh_d[i];
-        Ray r = make_ray(xyz(o), xyz(d));
-        TravStats st{0, 0};
-        vis[i] = light_visible<COUNT>(S, r, o.w, &st) ? 1 : 0;
-        if (COUNT) { nodes += st.nodes; prims += st.prims; }
+    const unsigned lane = threadIdx.x & 31u;
+    TravStats st{0, 0};
+    bool has = false, exhausted = false;
+    unsigned idx = 0;
+    float dist = 0.f;
+    Ray r;
+    ShadowTrav T;
+    r.o = r.d = r.inv = mk3(0, 0, 0);
+    shadow_begin(T, 0.f);
+    for (;;) {
+        if (!exhausted) {
+            unsigned need = __ballot_sync(0xffffffffu, !has);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                unsigned base = 0;
+                if ((int)lane == leader) base = atomicAdd(next, (unsigned)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!has) {
+                    idx = base + (unsigned)__popc(need & lanemask_lt());
+                    if (idx < n) {
+                        float4 o = sh_o[idx], d = sh_d[idx];
+                        r = make_ray(xyz(o), xyz(d));
+                        dist = o.w;
+                        shadow_begin(T, dist);
+                        has = true;
+                    }
+                }
+                exhausted = base + (unsigned)__popc(need) >= n;
+            }
+        }
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!act) break;
+        do {
+            if (has && !shadow_step<COUNT>(S, r, dist, T, &st)) {
+                vis[idx] = T.visible ? 1 : 0;
+                has = false;
+            }
+            act = __ballot_sync(0xffffffffu, has);
+        } while (act && (exhausted || __popc(act) > kRefillBelow));
     }
     if (COUNT) {
-        nodes = warp_sum(nodes); prims = warp_sum(prims);
-        if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
+        unsigned long long nodes = warp_sum((unsigned long long)st.nodes), prims = warp_sum((unsigned long long)st.prims);
+        if (lane == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
     }
 }
 
@@ -529,6 +601,8 @@ __global__ void swap_counts_kernel(Counters *cnt) {
     cnt->n_next = 0;
     cnt->n_shadow = 0;
     for (int c = 0; c < kClasses; ++c) cnt->n_class[c] = 0;
+    cnt->fetch_extend = 0;
+    cnt->fetch_shadow = 0;
 }
 
 // ---- batch kernels for the parity entry points ---------------------------------------------------------------
@@ -815,8 +889,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             if (n > ctx->wave_rays) return fail(ctx, B2PT_ERR_CUDA, "ray queue overflow (internal error)");
             Queue &qa = ctx->wb.q[cur], &qb = ctx->wb.q[cur ^ 1];
             CU(cudaEventRecord(ctx->ev[2], st));
-            if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
-            else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+            if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+            else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
             CU(cudaEventRecord(ctx->ev[3], st));
             launches++; ext_launches++;
             light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o,
@@ -824,8 +898,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             launches++;
             if (S.enable_shadow) {
                 CU(cudaEventRecord(ctx->ev[4], st));
-                if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, ctx->wb.vis, dc);
-                else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, ctx->wb.vis, dc);
+                if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
+                else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
                 CU(cudaEventRecord(ctx->ev[5], st));
                 launches++; sh_launches++;
             }

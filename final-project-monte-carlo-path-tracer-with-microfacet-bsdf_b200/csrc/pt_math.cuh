@@ -287,114 +287,142 @@ PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray 
 }
 
 // nodes[0] is the root and nodes[1] an EMPTY filler, so the walk starts at sibling pair 0.
-template <bool COUNT>
-PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
+// The walk is written as a state machine (begin / step) so that the persistent traversal kernels can
+// interleave the walks of a warp's lanes and hand a finished lane a new ray; closest_hit() below is
+// the plain loop over the same steps.
+struct Trav {
     Hit h;
-    h.t = 1.7976931348623157e308;  // Intersection::distance of a miss, src/Intersection.hpp:17
-    h.prim = -1;
-    float bound = INFINITY;
+    float bound;
+    uint32_t pair;
+    int sp;
     uint32_t stk[kStackSize];
     float stk_t[kStackSize];
-    int sp = 0;
-    uint32_t pair = 0;
-    for (;;) {
-        const float4 *p = S.nodes + 4 * (size_t)pair;
-        float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
-        if (COUNT) st->nodes += 2;
-        uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
-        float tl = 0.f, tr = 0.f;
-        bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > bound);
-        bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > bound);
-        if (hl && lk != NODE_INTERIOR) {
+};
+PT_HD void trav_begin(Trav &T) {
+    T.h.t = 1.7976931348623157e308;  // Intersection::distance of a miss, src/Intersection.hpp:17
+    T.h.prim = -1;
+    T.bound = INFINITY;
+    T.sp = 0;
+    T.pair = 0;
+}
+// One sibling pair.  Returns false when the walk has finished (T.h is the result).
+template <bool COUNT>
+PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
+    const float4 *p = S.nodes + 4 * (size_t)T.pair;
+    float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
+    if (COUNT) st->nodes += 2;
+    uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
+    float tl = 0.f, tr = 0.f;
+    bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
+    bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
+    if (hl && lk != NODE_INTERIOR) {
+        double t;
+        if (COUNT) st->prims++;
+        if (prim_hit(S, la, lk, r, &t) && (t < T.h.t || (t == T.h.t && (int)la > T.h.prim))) {
+            T.h.t = t; T.h.prim = (int)la; T.bound = prune_bound(t);
+        }
+        hl = false;
+    }
+    if (hr && rk != NODE_INTERIOR) {
+        if (!(tr > T.bound)) {
             double t;
             if (COUNT) st->prims++;
-            if (prim_hit(S, la, lk, r, &t) && (t < h.t || (t == h.t && (int)la > h.prim))) {
-                h.t = t; h.prim = (int)la; bound = prune_bound(t);
+            if (prim_hit(S, ra, rk, r, &t) && (t < T.h.t || (t == T.h.t && (int)ra > T.h.prim))) {
+                T.h.t = t; T.h.prim = (int)ra; T.bound = prune_bound(t);
             }
-            hl = false;
         }
-        if (hr && rk != NODE_INTERIOR) {
-            if (!(tr > bound)) {
-                double t;
-                if (COUNT) st->prims++;
-                if (prim_hit(S, ra, rk, r, &t) && (t < h.t || (t == h.t && (int)ra > h.prim))) {
-                    h.t = t; h.prim = (int)ra; bound = prune_bound(t);
-                }
-            }
-            hr = false;
-        }
-        if (hl && tl > bound) hl = false;
-        if (hr && tr > bound) hr = false;
-        if (hl && hr) {
-            bool left_near = !(tr < tl);
-            stk[sp] = left_near ? ra : la;
-            stk_t[sp] = left_near ? tr : tl;
-            sp++;
-            pair = left_near ? la : ra;
-            continue;
-        }
-        if (hl) { pair = la; continue; }
-        if (hr) { pair = ra; continue; }
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            if (!(stk_t[sp] > bound)) { pair = stk[sp]; found = true; break; }
-        }
-        if (!found) break;
+        hr = false;
     }
-    return h;
+    if (hl && tl > T.bound) hl = false;
+    if (hr && tr > T.bound) hr = false;
+    if (hl && hr) {
+        bool left_near = !(tr < tl);
+        T.stk[T.sp] = left_near ? ra : la;
+        T.stk_t[T.sp] = left_near ? tr : tl;
+        T.sp++;
+        T.pair = left_near ? la : ra;
+        return true;
+    }
+    if (hl) { T.pair = la; return true; }
+    if (hr) { T.pair = ra; return true; }
+    while (T.sp > 0) {
+        --T.sp;
+        if (!(T.stk_t[T.sp] > T.bound)) { T.pair = T.stk[T.sp]; return true; }
+    }
+    return false;
+}
+template <bool COUNT>
+PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
+    Trav T;
+    trav_begin(T);
+    while (trav_step<COUNT>(S, r, T, st)) {}
+    return T.h;
 }
 
 // ---- visibility of a light sample: Scene::directLighting, src/Scene.cpp:72-75 -----------------------------
 // visible <=> the CLOSEST hit exists and |distance - dist| < EPSILON (compared in double).  Equivalent
 // without finding the closest hit: no hit with t <= dist - EPSILON exists (early exit when one is
 // found) and some hit lies inside the window; subtrees entered beyond the window are skipped.
+struct ShadowTrav {
+    bool in_window, visible;
+    float bound;
+    uint32_t pair;
+    int sp;
+    uint32_t stk[kStackSize];
+};
+PT_HD void shadow_begin(ShadowTrav &T, float dist) {
+    T.in_window = false; T.visible = false;
+    T.bound = dist + (4e-3f + 1e-5f * dist);
+    T.sp = 0;
+    T.pair = 0;
+}
+// Returns false when the decision is known (T.visible).
+template <bool COUNT>
+PT_HD bool shadow_step(const SceneView &S, const Ray &r, float dist, ShadowTrav &T, TravStats *st) {
+    const double eps = (double)kEps, dd = (double)dist;
+    const float4 *p = S.nodes + 4 * (size_t)T.pair;
+    float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
+    if (COUNT) st->nodes += 2;
+    uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
+    float tl = 0.f, tr = 0.f;
+    bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
+    bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
+    if (hl && lk != NODE_INTERIOR) {
+        double t;
+        if (COUNT) st->prims++;
+        if (prim_hit(S, la, lk, r, &t)) {
+            if (fabs(t - dd) < eps) T.in_window = true;
+            else if (t < dd) { T.visible = false; return false; }  // a closer hit outside the window: the closest hit fails the test
+        }
+        hl = false;
+    }
+    if (hr && rk != NODE_INTERIOR) {
+        double t;
+        if (COUNT) st->prims++;
+        if (prim_hit(S, ra, rk, r, &t)) {
+            if (fabs(t - dd) < eps) T.in_window = true;
+            else if (t < dd) { T.visible = false; return false; }
+        }
+        hr = false;
+    }
+    if (hl && hr) {
+        bool left_near = !(tr < tl);
+        T.stk[T.sp++] = left_near ? ra : la;
+        T.pair = left_near ? la : ra;
+        return true;
+    }
+    if (hl) { T.pair = la; return true; }
+    if (hr) { T.pair = ra; return true; }
+    if (T.sp == 0) { T.visible = T.in_window; return false; }
+    T.pair = T.stk[--T.sp];
+    return true;
+}
 template <bool COUNT>
 PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st) {
-    const double eps = (double)kEps, dd = (double)dist;
-    const float bound = dist + (4e-3f + 1e-5f * dist);
-    bool in_window = false;
-    uint32_t stk[kStackSize];
-    int sp = 0;
-    uint32_t pair = 0;
-    for (;;) {
-        const float4 *p = S.nodes + 4 * (size_t)pair;
-        float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
-        if (COUNT) st->nodes += 2;
-        uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
-        float tl = 0.f, tr = 0.f;
-        bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > bound);
-        bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > bound);
-        if (hl && lk != NODE_INTERIOR) {
-            double t;
-            if (COUNT) st->prims++;
-            if (prim_hit(S, la, lk, r, &t)) {
-                if (fabs(t - dd) < eps) in_window = true;
-                else if (t < dd) return false;  // a closer hit outside the window: the closest hit fails the test
-            }
-            hl = false;
-        }
-        if (hr && rk != NODE_INTERIOR) {
-            double t;
-            if (COUNT) st->prims++;
-            if (prim_hit(S, ra, rk, r, &t)) {
-                if (fabs(t - dd) < eps) in_window = true;
-                else if (t < dd) return false;
-            }
-            hr = false;
-        }
-        if (hl && hr) {
-            bool left_near = !(tr < tl);
-            stk[sp++] = left_near ? ra : la;
-            pair = left_near ? la : ra;
-            continue;
-        }
-        if (hl) { pair = la; continue; }
-        if (hr) { pair = ra; continue; }
-        if (sp == 0) break;
-        pair = stk[--sp];
-    }
-    return in_window;
+    ShadowTrav T;
+    shadow_begin(T, dist);
+    while (shadow_step<COUNT>(S, r, dist, T, st)) {}
+    return T.visible;
 }
 
 // ---- surface point of a hit: the Intersection the reference returns ---------------------------------------
