@@ -197,8 +197,11 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
+    from b2pt.multigpu import reduce_frame, sample_range
+
     S_step = args.spp_per_step
     spp_total = S_step * world  # samples per pixel of one step's frame
+    my_begin, my_count = sample_range(rank, world, spp_total)
     fb = torch.zeros((cam.height, cam.width, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_fb = torch.zeros((cam.height, cam.width, 3), dtype=torch.float32).pin_memory()
@@ -211,9 +214,8 @@ def run_ours(args):
 
     def step_device(step, flags=0):
         fb.zero_()
-        st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=rank * S_step, sample_count=S_step, seed=S.SEED + step, flags=flags)
-        if dist is not None:
-            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+        st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step, flags=flags)
+        reduce_frame(fb, dist, 0)
         return st
 
     def step_e2e(step):
@@ -222,8 +224,8 @@ def run_ours(args):
             _, st = ctx.render(cam, spp_total, seed=S.SEED + step, sample_begin=0, sample_count=S_step, out=host_np)
         else:
             fb.copy_(host_fb, non_blocking=True)
-            st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=rank * S_step, sample_count=S_step, seed=S.SEED + step)
-            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+            st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step)
+            reduce_frame(fb, dist, 0)
             if rank == 0:
                 host_fb.copy_(fb, non_blocking=True)
             torch.cuda.synchronize(dev)

@@ -1,0 +1,111 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties (the oracle cannot render 1080p x 2048 spp
+in test time): sample ranges compose, wave size and wavelength sharing do not change the frame, ray accounting is
+consistent, and a crop of the full-size frame is statistically equivalent to the oracle's render of the same pixels."""
+import numpy as np
+import pytest
+
+import scenes
+import support as S
+
+b2pt = S.b2pt
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b2pt.Context(0)
+    yield c
+    c.close()
+
+
+def test_chess_1080p_properties(ctx):
+    """configs[1] geometry at 1920x1080 (spp reduced): composition, determinism, accounting."""
+    sc, env = scenes.chess(1920, 1080, dof=True, sky=True)
+    ctx.upload(sc)
+    cam = sc.camera
+    spp = 4
+    full, st = ctx.render(cam, spp)
+    assert full.shape == (1080, 1920, 3) and np.isfinite(full).all()
+    assert st.bundles == 1920 * 1080 * spp and st.paths == 3 * st.bundles
+    # rays per path of the chess scene at N=4 (SURVEY 8d measured 2.77 on the CPU with a black background)
+    rpp = st.rays_reference / st.paths
+    assert 2.3 < rpp < 3.4, rpp
+    assert st.rays_traced_closest + st.rays_traced_shadow < st.rays_reference  # sharing: fewer traversals than reference rays
+    # (i) two half-frames on different "ranks" sum to the frame
+    acc, _ = ctx.render(cam, spp, sample_begin=0, sample_count=1)
+    acc, _ = ctx.render(cam, spp, sample_begin=1, sample_count=3, out=acc)
+    assert np.allclose(acc, full, rtol=2e-5, atol=2e-6)
+    # (ii) wave size does not matter; (iii) nor does sharing rays between wavelengths
+    small, st_small = ctx.render(cam, spp, max_wave_bundles=1 << 20)
+    assert st_small.waves > st.waves and st_small.rays_reference == st.rays_reference
+    assert np.allclose(small, full, rtol=2e-5, atol=2e-6)
+    split, st_split = ctx.render(cam, spp, flags=b2pt.FLAG_SPLIT_WAVELENGTHS)
+    assert st_split.rays_reference == st.rays_reference and st_split.rays_traced_closest > st.rays_traced_closest
+    assert np.allclose(split, full, rtol=2e-5, atol=2e-6)
+    # (iv) the image is where it should be: sky at the top, lit floor at the bottom
+    assert full[:100].mean() > 0.3 and full[-200:].mean() > 0.01
+    sc.close()
+
+
+@pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref/libref_oracle.so not built")
+@pytest.mark.parametrize("which", ["chess_dof_sky", "chess_dark", "cornell512"])
+def test_crop_statistically_equivalent_to_oracle(ctx, which):
+    """(c) of the north star: per-pixel 99% confidence intervals and RMSE vs the oracle, on a pixel subset of the full frame.
+    GPU and oracle use DIFFERENT seeds here, so this is a statistical, not a replay, comparison."""
+    if which == "cornell512":
+        sc, env = scenes.cornell(512, 512)
+    else:
+        sc, env = scenes.chess(1920, 1080, dof=which == "chess_dof_sky", sky=which == "chess_dof_sky")
+    ctx.upload(sc)
+    ref = S.Ref(sc, env)
+    cam = sc.camera
+    rng = np.random.RandomState(3)
+    px = rng.choice(cam.width * cam.height, 160, replace=False).astype(np.int32)
+    n = 96
+    g, _ = ctx.render_samples(cam, px, 0, n, seed=0xABCDEF01)
+    r = ref.render_samples(px, 0, n, seed=0x12345678)
+    gm, rm = g.mean(1), r.mean(1)
+    se = np.sqrt(g.var(1, ddof=1) / n + r.var(1, ddof=1) / n)
+    z = np.abs(gm - rm) / np.maximum(se, 1e-6)
+    inside = (z < 2.576) | (np.abs(gm - rm) < 1e-4)
+    assert inside.mean() > 0.97, f"{which}: only {inside.mean() * 100:.1f}% of pixel-channel means inside the 99% interval"
+    rmse = np.sqrt(np.mean((gm - rm) ** 2))
+    noise = np.sqrt(np.mean(se ** 2))
+    assert rmse < 1.5 * noise + 1e-4, (rmse, noise)
+    assert abs(gm.mean() - rm.mean()) < 0.05 * max(rm.mean(), 1e-3) + 3 * noise / np.sqrt(gm.size)
+    ref.close(); sc.close()
+
+
+def test_material_sweep_cornell(ctx):
+    """configs[4]: each of the nine materials on the Cornell spheres and boxes renders finite, non-degenerate frames, and the
+    per-sample values replay against the oracle."""
+    if not S.have_ref():
+        pytest.skip("oracle not built")
+    for mi, name in enumerate(b2pt.NAMED_MATERIALS):
+        sc = b2pt.HostScene.demo(128, 128)
+        # objects: floor, shortbox, tallbox, left, right, light, 3 spheres
+        L = b2pt.host_lib()
+        desc_before = [sc.object_info(k) for k in range(sc.n_objects)]
+        sc.close()
+        sc = b2pt.HostScene.empty()
+        light = sc.add_material("light", b2pt.Material(b2pt.ROUGH_CONDUCTOR, tuple(47.8348 * 3.9 * x / 47.8348 for x in (47.8348, 38.5664, 31.0808)), 1.74, 0.1, 1.0, (0, 0, 0), 0, 0))
+        for k, o in enumerate(desc_before):
+            if o["kind"] == "sphere":
+                sc.add_sphere(o["center"], o["radius"], mi)
+            elif k in (1, 2):
+                sc.add_triangles(o["v9"], mi)
+            elif k == 5:
+                sc.add_triangles(o["v9"], light)
+            else:
+                sc.add_triangles(o["v9"], o["material"])
+        sc.set_camera(128, 128, 40.0, (278, 273, -800), (278, 273, 0))
+        sc.build_tree()
+        ctx.upload(sc)
+        ref = S.Ref(sc)
+        px = np.arange(0, 128 * 128, 37, dtype=np.int32)
+        g, _ = ctx.render_samples(sc.camera, px, 0, 4)
+        r = ref.render_samples(px, 0, 4)
+        ok = np.abs(g - r) <= 1e-5 + 2e-4 * np.maximum(np.abs(g), np.abs(r))
+        assert ok.mean() >= 0.999, (name, (~ok).sum())
+        assert np.isfinite(g).all() and g.mean() > 0.01, name
+        ref.close(); sc.close()
