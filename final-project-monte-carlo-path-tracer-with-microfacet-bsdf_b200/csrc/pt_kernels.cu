@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBlock) extend_kernel(SceneView S, const float
     Ray r;
     Trav T;
     r.o = r.d = r.inv = mk3(0, 0, 0);
-    trav_begin(T);
+    trav_begin(S, r, T);
     for (;;) {
         if (!exhausted) {
             unsigned need = __ballot_sync(0xffffffffu, !has);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kBlock) extend_kernel(SceneView S, const float
                     if (idx < n) {
                         float4 o = qo[idx], d = qd[idx];
                         r = make_ray(xyz(o), xyz(d));
-                        trav_begin(T);
+                        trav_begin(S, r, T);
                         has = true;
                         refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
                     }
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
     Ray r;
     ShadowTrav T;
     r.o = r.d = r.inv = mk3(0, 0, 0);
-    shadow_begin(T, 0.f);
+    shadow_begin(S, r, T, 0.f);
     for (;;) {
         if (!exhausted) {
             unsigned need = __ballot_sync(0xffffffffu, !has);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
                         float4 o = sh_o[idx], d = sh_d[idx];
                         r = make_ray(xyz(o), xyz(d));
                         dist = o.w;
-                        shadow_begin(T, dist);
+                        shadow_begin(S, r, T, dist);
                         has = true;
                     }
                 }
@@ -1061,7 +1061,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     free_scene(ctx);
     PackedScene packed;
     pack_scene(d, packed);
-    ctx->scene_bufs.resize(18);
+    ctx->scene_bufs.resize(19);
     auto up = [&](int slot, const void *src, size_t bytes) -> void * {
         if (upload(ctx, ctx->scene_bufs[slot], src, bytes)) return nullptr;
         return ctx->scene_bufs[slot].p;
@@ -1070,7 +1070,8 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     const size_t np = d->n_prims;
     bool ok = true;
 #define UP(field, type, slot, src, bytes) ok = ok && ((v.field = (type)up(slot, src, bytes)) != nullptr)
-    UP(nodes, const float4 *, 0, d->nodes, sizeof(b2pt_node) * (size_t)d->n_nodes);
+    UP(nodes_ref, const float4 *, 0, packed.nodes_ref.data(), sizeof(b2pt_node) * packed.nodes_ref.size());
+    UP(nodes, const float4 *, 18, packed.nodes_fast.data(), sizeof(b2pt_node) * packed.nodes_fast.size());
     UP(v0, const float4 *, 1, d->prim_v0, 16 * np);
     UP(e1, const float4 *, 2, d->prim_e1, 16 * np);
     UP(e2, const float4 *, 3, d->prim_e2, 16 * np);

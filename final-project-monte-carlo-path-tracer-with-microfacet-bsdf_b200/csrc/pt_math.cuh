@@ -33,7 +33,7 @@ namespace pt {
 
 constexpr float kEps = 1e-4f;                  // EPSILON, src/Renderer.cpp:15
 constexpr float kPi = 3.141592653589793f;      // M_PI redefined as float, src/global.hpp:8-9
-constexpr int kStackSize = 40;
+constexpr int kStackSize = 48;
 
 enum { MAT_SMOOTH_CONDUCTOR = 0, MAT_ROUGH_CONDUCTOR = 1, MAT_SMOOTH_DIELECTRIC = 2, MAT_ROUGH_DIELECTRIC = 3 };
 enum { NODE_INTERIOR = 0, NODE_TRIANGLE = 1, NODE_SPHERE = 2, NODE_EMPTY = 3 };
@@ -160,7 +160,10 @@ struct Material {
     int emissive;  // Material::hasEmission(), src/Material.hpp:263
 };
 struct SceneView {
-    const float4 *nodes;    // 2 float4 per node: (bmin, a) (bmax, kind)
+    const float4 *nodes;      // traversal tree built by pt_build.hpp (binned SAH over the reference's leaves); 2 float4 per node:
+                              // (bmin, a) (bmax, kind); EMPTY nodes carry NaN boxes, which fail the box test by themselves
+    const float4 *nodes_ref;  // the reference's own topology (src/BVH.cpp:27-93), same layout: used by rays whose slab
+                              // products can be NaN (see ray_needs_reference_tree) and by the parity entry points
     const float4 *v0, *e1, *e2, *nrm;  // per primitive
     const float *v1v2, *uv;            // 6 floats per primitive
     const uint32_t *prim_mat, *prim_kind;
@@ -197,31 +200,43 @@ PT_HD bool box_hit(f3 pmin, f3 pmax, const Ray &r, float *tmin_out) {
     float t2x = (pmax.x - r.o.x) * r.inv.x, t2y = (pmax.y - r.o.y) * r.inv.y, t2z = (pmax.z - r.o.z) * r.inv.z;
     float mnx = fminf(t1x, t2x), mny = fminf(t1y, t2y), mnz = fminf(t1z, t2z);
     float mxx = fmaxf(t1x, t2x), mxy = fmaxf(t1y, t2y), mxz = fmaxf(t1z, t2z);
-    // std::max({a,b,c}) / std::min({a,b,c}): sequential `<` comparisons (NaN keeps the running value)
-    float tmin = mnx;
-    if (tmin < mny) tmin = mny;
-    if (tmin < mnz) tmin = mnz;
-    float tmax = mxx;
-    if (mxy < tmax) tmax = mxy;
-    if (mxz < tmax) tmax = mxz;
+    // std::max({a,b,c}) / std::min({a,b,c}) are sequential `<` comparisons: a NaN in a LATER element is skipped (like
+    // fmaxf / fminf), a NaN in the FIRST element stays to the end and fails the test.  mnx is NaN iff mxx is NaN
+    // (both slab products of the x axis are NaN), so one extra check restores the reference's behaviour.
+    float tmin = fmaxf(fmaxf(mnx, mny), mnz);
+    float tmax = fminf(fminf(mxx, mxy), mxz);
     *tmin_out = tmin;
-    return (tmin - kEps <= tmax) && (tmax >= -kEps);
+    return (tmin - kEps <= tmax) && (tmax >= -kEps) && (mnx == mnx);
 }
 
 // ---- Triangle::getIntersection, src/Triangle.hpp:222-252 ---------------------------------------------
 // float cross / dot products, then det_inv, u, v, t in double.
+// Rejections that need no FP64 are taken first: u, v and t are products of a float dot product with det_inv = 1./det,
+// so each is negative exactly when its dot product and det have strictly opposite signs, and u > 1 (u + v > 1) is
+// certain when |a| (|a| + |b|) exceeds |det| by more than any rounding of the double products.  Everything that
+// survives goes through the reference's arithmetic unchanged, so hits and their t are bit-identical.
+PT_HD bool opposite_signs(float a, float det) { return (a < 0.f && det > 0.f) || (a > 0.f && det < 0.f); }
 PT_HD bool tri_hit(f3 v0, f3 e1, f3 e2, const Ray &r, double *t_out, double *u_out, double *v_out) {
     f3 pvec = cross(r.d, e2);
-    double det = (double)dot(e1, pvec);
-    if (fabs(det) < (double)kEps) return false;
-    double det_inv = 1. / det;
+    float det_f = dot(e1, pvec);
+    if (fabsf(det_f) < kEps) return false;  // fabs((double)det) < (double)EPSILON, exact in float
     f3 tvec = r.o - v0;
-    double u = (double)dot(tvec, pvec) * det_inv;
-    if (u < 0 || u > 1) return false;
+    float a = dot(tvec, pvec);
+    if (opposite_signs(a, det_f)) return false;  // u < 0
     f3 qvec = cross(tvec, e1);
-    double v = (double)dot(r.d, qvec) * det_inv;
+    float b = dot(r.d, qvec);
+    if (opposite_signs(b, det_f)) return false;  // v < 0
+    float c = dot(e2, qvec);
+    if (opposite_signs(c, det_f)) return false;  // t < 0
+    float ad = fabsf(det_f) * 1.00001f;
+    if (fabsf(a) > ad || fabsf(a) + fabsf(b) > ad * 1.00001f) return false;  // u > 1 or u + v > 1 beyond rounding
+    double det = (double)det_f;
+    double det_inv = 1. / det;
+    double u = (double)a * det_inv;
+    if (u < 0 || u > 1) return false;
+    double v = (double)b * det_inv;
     if (v < 0 || u + v > 1) return false;
-    double t = (double)dot(e2, qvec) * det_inv;
+    double t = (double)c * det_inv;
     if (t < 0) return false;
     *t_out = t; *u_out = u; *v_out = v;
     return true;
@@ -290,15 +305,25 @@ PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray 
 // The walk is written as a state machine (begin / step) so that the persistent traversal kernels can
 // interleave the walks of a warp's lanes and hand a finished lane a new ray; closest_hit() below is
 // the plain loop over the same steps.
+// The traversal tree may be any tree over the reference's leaf boxes (pt_build.hpp explains why the hits are the same)
+// as long as no slab product (p - o) * inv is NaN.  NaN needs an infinite inverse direction component (a zero or
+// denormal direction component) or a non-finite origin: those rays walk the reference's own topology instead.
+PT_HD bool ray_needs_reference_tree(const Ray &r) {
+    float s = (fabsf(r.inv.x) + fabsf(r.inv.y)) + fabsf(r.inv.z);
+    float q = (fabsf(r.o.x) + fabsf(r.o.y)) + fabsf(r.o.z);
+    return !(s < INFINITY) || !(q < INFINITY);
+}
 struct Trav {
     Hit h;
+    const float4 *nodes;
     float bound;
     uint32_t pair;
     int sp;
     uint32_t stk[kStackSize];
     float stk_t[kStackSize];
 };
-PT_HD void trav_begin(Trav &T) {
+PT_HD void trav_begin(const SceneView &S, const Ray &r, Trav &T) {
+    T.nodes = ray_needs_reference_tree(r) ? S.nodes_ref : S.nodes;
     T.h.t = 1.7976931348623157e308;  // Intersection::distance of a miss, src/Intersection.hpp:17
     T.h.prim = -1;
     T.bound = INFINITY;
@@ -308,13 +333,13 @@ PT_HD void trav_begin(Trav &T) {
 // One sibling pair.  Returns false when the walk has finished (T.h is the result).
 template <bool COUNT>
 PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
-    const float4 *p = S.nodes + 4 * (size_t)T.pair;
+    const float4 *p = T.nodes + 4 * (size_t)T.pair;
     float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
     if (COUNT) st->nodes += 2;
     uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
     float tl = 0.f, tr = 0.f;
-    bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
-    bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
+    bool hl = box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
+    bool hr = box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
     if (hl && lk != NODE_INTERIOR) {
         double t;
         if (COUNT) st->prims++;
@@ -354,7 +379,7 @@ PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
 template <bool COUNT>
 PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
     Trav T;
-    trav_begin(T);
+    trav_begin(S, r, T);
     while (trav_step<COUNT>(S, r, T, st)) {}
     return T.h;
 }
@@ -364,13 +389,15 @@ PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
 // without finding the closest hit: no hit with t <= dist - EPSILON exists (early exit when one is
 // found) and some hit lies inside the window; subtrees entered beyond the window are skipped.
 struct ShadowTrav {
+    const float4 *nodes;
     bool in_window, visible;
     float bound;
     uint32_t pair;
     int sp;
     uint32_t stk[kStackSize];
 };
-PT_HD void shadow_begin(ShadowTrav &T, float dist) {
+PT_HD void shadow_begin(const SceneView &S, const Ray &r, ShadowTrav &T, float dist) {
+    T.nodes = ray_needs_reference_tree(r) ? S.nodes_ref : S.nodes;
     T.in_window = false; T.visible = false;
     T.bound = dist + (4e-3f + 1e-5f * dist);
     T.sp = 0;
@@ -380,13 +407,13 @@ PT_HD void shadow_begin(ShadowTrav &T, float dist) {
 template <bool COUNT>
 PT_HD bool shadow_step(const SceneView &S, const Ray &r, float dist, ShadowTrav &T, TravStats *st) {
     const double eps = (double)kEps, dd = (double)dist;
-    const float4 *p = S.nodes + 4 * (size_t)T.pair;
+    const float4 *p = T.nodes + 4 * (size_t)T.pair;
     float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
     if (COUNT) st->nodes += 2;
     uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
     float tl = 0.f, tr = 0.f;
-    bool hl = (lk != NODE_EMPTY) && box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
-    bool hr = (rk != NODE_EMPTY) && box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
+    bool hl = box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
+    bool hr = box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
     if (hl && lk != NODE_INTERIOR) {
         double t;
         if (COUNT) st->prims++;
@@ -420,7 +447,7 @@ PT_HD bool shadow_step(const SceneView &S, const Ray &r, float dist, ShadowTrav 
 template <bool COUNT>
 PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st) {
     ShadowTrav T;
-    shadow_begin(T, dist);
+    shadow_begin(S, r, T, dist);
     while (shadow_step<COUNT>(S, r, dist, T, st)) {}
     return T.visible;
 }

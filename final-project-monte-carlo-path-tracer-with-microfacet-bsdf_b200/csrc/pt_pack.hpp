@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "b2pt.h"
+#include "pt_build.hpp"
 #include "pt_math.cuh"
 
 namespace pt {
@@ -15,6 +16,9 @@ namespace pt {
 struct PackedScene {
     std::vector<Material> mats;
     std::vector<float4> env;
+    std::vector<b2pt_node> nodes_ref;   // the reference's topology, EMPTY boxes rewritten to NaN
+    std::vector<b2pt_node> nodes_fast;  // binned-SAH tree over the same leaves (pt_build.hpp)
+    int fast_depth = 0;
 };
 
 inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
@@ -47,7 +51,19 @@ inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
     return true;
 }
 
-inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out) {
+inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fast_tree = true) {
+    out.nodes_ref.assign(d->nodes, d->nodes + d->n_nodes);
+    for (auto &n : out.nodes_ref)
+        if (n.kind == B2PT_NODE_EMPTY)
+            for (int k = 0; k < 3; ++k) { n.bmin[k] = NAN; n.bmax[k] = NAN; }
+    out.nodes_fast.clear();
+    out.fast_depth = 0;
+    if (build_fast_tree) {
+        SahBuilder b;
+        b.run(d);
+        if (b.max_depth + 2 < kStackSize) { out.nodes_fast.swap(b.out); out.fast_depth = b.max_depth; }
+    }
+    if (out.nodes_fast.empty()) { out.nodes_fast = out.nodes_ref; out.fast_depth = (int)d->max_depth; }
     out.mats.resize(d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const b2pt_material &s = d->materials[i];

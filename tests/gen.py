@@ -19,12 +19,15 @@ def adversarial_triangle_cases(rng, n):
     o = (rng.rand(n, 3).astype(np.float32) - 0.5) * np.float32(400)
     # aim at a point of the triangle's plane: inside, on edges, at vertices, just outside
     w = rng.rand(n, 2).astype(np.float32)
-    kind = rng.randint(0, 5, n)
+    kind = rng.randint(0, 8, n)
     w[kind == 1, 1] = 0            # on edge
     w[kind == 2] = 0               # at vertex v0
     w[kind == 3] *= np.float32(1.5)  # may leave the triangle
     flip = w.sum(1) > 1
     w[flip & (kind != 3)] = 1 - w[flip & (kind != 3)]
+    w[kind == 5, 1] = 1 - w[kind == 5, 0]   # on the far edge: u + v == 1 up to rounding
+    w[kind == 6] = [1, 0]                   # at v1: u == 1
+    w[kind == 7] = [0, 1]                   # at v2: v == 1
     v0, v1, v2 = v[:, 0:3], v[:, 3:6], v[:, 6:9]
     p = v0 + (v1 - v0) * w[:, :1] + (v2 - v0) * w[:, 1:]
     d = p - o
@@ -74,3 +77,25 @@ def sphere_cases(rng, n):
     d = tgt - o
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     return c4, o, d.astype(np.float32)
+
+
+def degenerate_rays(rng, scene_min, scene_max, n):
+    """Rays whose slab products can be NaN or infinite: zero direction components, origins on axis-aligned planes
+    (y = 0 is the chess floor / Cornell floor), zero-length directions (what Material::refract returns on total
+    internal reflection), denormal components."""
+    lo, hi = np.asarray(scene_min, np.float32), np.asarray(scene_max, np.float32)
+    o = (lo + (hi - lo) * rng.rand(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    k = rng.randint(0, 6, n)
+    d[k == 0, 0] = 0
+    d[k == 1, 1] = 0
+    d[k == 2, 2] = 0
+    d[k == 3] = d[k == 3] * np.array([1, 0, 0], np.float32)   # axis-parallel
+    d[k == 4] = 0                                              # zero vector
+    d[k == 5, 1] = np.float32(1e-41)                           # denormal: 1/d overflows to inf
+    nz = np.linalg.norm(d, axis=1) > 0
+    d[nz] /= np.linalg.norm(d[nz], axis=1, keepdims=True)
+    d[k == 5, 1] = np.float32(1e-41)
+    on_plane = rng.rand(n) < 0.5
+    o[on_plane, 1] = 0                                         # exactly on the floor plane
+    return o, d.astype(np.float32)

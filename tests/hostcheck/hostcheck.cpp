@@ -16,7 +16,7 @@ using namespace pt;
 
 struct HcScene {
     PackedScene packed;
-    std::vector<float4> nodes, v0, e1, e2, nrm;
+    std::vector<float4> nodes, nodes_ref, v0, e1, e2, nrm;
     std::vector<float> v1v2, uv, light_area, ln_area;
     std::vector<uint32_t> prim_mat, prim_kind, light_root, light_mat;
     std::vector<int> ln_left, ln_right, ln_prim;
@@ -26,13 +26,15 @@ static inline f3 V(const float *p) { return mk3(p[0], p[1], p[2]); }
 
 extern "C" {
 
-void *hc_scene_new(const b2pt_scene_desc *d) {
+static void *scene_new(const b2pt_scene_desc *d, bool fast) {
     std::string err;
     if (!validate_scene(d, err)) return nullptr;
     HcScene *h = new HcScene();
-    pack_scene(d, h->packed);
-    h->nodes.resize(2 * (size_t)d->n_nodes);
-    std::memcpy(h->nodes.data(), d->nodes, sizeof(b2pt_node) * d->n_nodes);
+    pack_scene(d, h->packed, fast);
+    h->nodes.resize(2 * h->packed.nodes_fast.size());
+    std::memcpy(h->nodes.data(), h->packed.nodes_fast.data(), sizeof(b2pt_node) * h->packed.nodes_fast.size());
+    h->nodes_ref.resize(2 * h->packed.nodes_ref.size());
+    std::memcpy(h->nodes_ref.data(), h->packed.nodes_ref.data(), sizeof(b2pt_node) * h->packed.nodes_ref.size());
     auto cp4 = [&](std::vector<float4> &dst, const float *src) { dst.resize(d->n_prims); std::memcpy(dst.data(), src, 16 * (size_t)d->n_prims); };
     cp4(h->v0, d->prim_v0); cp4(h->e1, d->prim_e1); cp4(h->e2, d->prim_e2); cp4(h->nrm, d->prim_normal);
     h->v1v2.assign(d->prim_v1v2, d->prim_v1v2 + 6 * (size_t)d->n_prims);
@@ -47,7 +49,7 @@ void *hc_scene_new(const b2pt_scene_desc *d) {
     h->ln_right.assign(d->light_node_right, d->light_node_right + d->n_light_nodes);
     h->ln_prim.assign(d->light_node_prim, d->light_node_prim + d->n_light_nodes);
     SceneView &v = h->view;
-    v.nodes = h->nodes.data(); v.v0 = h->v0.data(); v.e1 = h->e1.data(); v.e2 = h->e2.data(); v.nrm = h->nrm.data();
+    v.nodes = h->nodes.data(); v.nodes_ref = h->nodes_ref.data(); v.v0 = h->v0.data(); v.e1 = h->e1.data(); v.e2 = h->e2.data(); v.nrm = h->nrm.data();
     v.v1v2 = h->v1v2.data(); v.uv = h->uv.data(); v.prim_mat = h->prim_mat.data(); v.prim_kind = h->prim_kind.data();
     v.mats = h->packed.mats.data();
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
@@ -57,6 +59,11 @@ void *hc_scene_new(const b2pt_scene_desc *d) {
     v.rr_rate = d->rr_rate; v.inv_rr = d->inv_rr; v.enable_shadow = d->enable_shadow; v.n_dir = d->n_dir_sample;
     return h;
 }
+// fast = 1: the library's traversal tree (pt_build.hpp); 0: the reference's topology only
+void *hc_scene_new2(const b2pt_scene_desc *d, int fast) { return scene_new(d, fast != 0); }
+void *hc_scene_new(const b2pt_scene_desc *d) { return scene_new(d, true); }
+int hc_fast_depth(void *h) { return ((HcScene *)h)->packed.fast_depth; }
+long hc_fast_nodes(void *h) { return (long)((HcScene *)h)->packed.nodes_fast.size(); }
 void hc_scene_free(void *h) { delete (HcScene *)h; }
 
 void hc_intersect(void *h, const float *o, const float *d, long n, int *prim, double *t, unsigned long long *counts) {

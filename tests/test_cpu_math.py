@@ -6,7 +6,7 @@ import pytest
 
 import scenes
 import support as S
-from gen import adversarial_triangle_cases, bsdf_inputs, box_cases, rel_close, sphere_cases, uniforms
+from gen import adversarial_triangle_cases, bsdf_inputs, box_cases, degenerate_rays, rel_close, sphere_cases, uniforms
 
 b2pt = S.b2pt
 pytestmark = pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref/libref_oracle.so not built")
@@ -66,6 +66,18 @@ def test_scene_intersect_bit_exact(world):
     assert np.array_equal(co_h[hit].view(np.uint32), co_r[hit].view(np.uint32))
     assert np.array_equal(nn_h[hit].view(np.uint32), nn_r[hit].view(np.uint32))
     assert nodes > 0 and prims > 0
+
+
+def test_degenerate_rays_take_the_reference_tree(world):
+    """Zero / denormal direction components and origins on box planes: slab products are NaN or infinite."""
+    name, sc, ref, hc = world
+    root = sc.desc.nodes[0]
+    o, d = degenerate_rays(np.random.RandomState(31), list(root.bmin), list(root.bmax), 4000)
+    prim_r, t_r, *_ = ref.intersect(o, d)
+    prim_h, t_h = hc.intersect(o, d)
+    assert np.array_equal(prim_h, prim_r), f"{name}: {(prim_h != prim_r).sum()} hit ids differ"
+    assert np.array_equal(t_h.view(np.uint64), t_r.view(np.uint64))
+    assert (prim_r >= 0).mean() > 0.05
 
 
 def test_textured_uv(world):

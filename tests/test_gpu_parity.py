@@ -9,7 +9,7 @@ import pytest
 
 import scenes
 import support as S
-from gen import adversarial_triangle_cases, bsdf_inputs, box_cases, rel_close, sphere_cases, uniforms
+from gen import adversarial_triangle_cases, bsdf_inputs, box_cases, degenerate_rays, rel_close, sphere_cases, uniforms
 
 b2pt = S.b2pt
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref/libref_oracle.so not built")]
@@ -83,6 +83,17 @@ def test_scene_intersect_bit_exact(ctx, world):
     assert np.array_equal(t_g.view(np.uint64), t_r.view(np.uint64))
     assert (prim_r >= 0).mean() > 0.3
     assert st.nodes_fetched > 0 and st.prims_tested > 0
+
+
+def test_degenerate_rays_take_the_reference_tree(ctx, world):
+    """Zero / denormal direction components and origins on box planes: slab products are NaN or infinite."""
+    name, sc, ref = world
+    root = sc.desc.nodes[0]
+    o, d = degenerate_rays(np.random.RandomState(31), list(root.bmin), list(root.bmax), 20000)
+    prim_r, t_r, *_ = ref.intersect(o, d)
+    prim_g, t_g = ctx.intersect(o, d)
+    assert np.array_equal(prim_g, prim_r), f"{name}: {(prim_g != prim_r).sum()} hit ids differ"
+    assert np.array_equal(t_g.view(np.uint64), t_r.view(np.uint64))
 
 
 def test_shadow_decision(ctx, world):
