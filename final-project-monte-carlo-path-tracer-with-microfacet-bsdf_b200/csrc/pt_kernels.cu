@@ -133,7 +133,9 @@ __device__ __forceinline__ Phi phi_compose(const Phi &p, float A, float f) {
 }
 
 // ---- generate: Renderer.cpp:39-76 -----------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams gp, Queue q, Counters *cnt) {
+// Appends to queue `q`, whose length lives in *count (path regeneration: new camera rays top up the queue
+// every bounce, so the kernels keep working on full queues until the samples run out).
+__global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams gp, Queue q, unsigned *count) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long rounded = ((unsigned long long)gp.count + kBlock - 1) / kBlock * kBlock;
     for (unsigned long long it = (unsigned long long)blockIdx.x * kBlock; it < rounded; it += (unsigned long long)gridDim.x * kBlock) {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
         const int per = gp.split ? 3 : 1;
         unsigned ballot = __ballot_sync(0xffffffffu, valid);
         unsigned base = 0;
-        if (lane == 0 && ballot) base = atomicAdd(&cnt->n_next, (unsigned)(__popc(ballot) * per));
+        if (lane == 0 && ballot) base = atomicAdd(count, (unsigned)(__popc(ballot) * per));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (valid) {
             unsigned p = base + (unsigned)__popc(ballot & lanemask_lt()) * per;
@@ -873,57 +875,62 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     unsigned long long launches = 0, ext_launches = 0, sh_launches = 0;
     unsigned waves = 0;
     Counters *dc = ctx->d_cnt;
-    for (unsigned long long first = 0; first < total; first += wave) {
-        gp.first = first;
-        gp.count = (unsigned)std::min<unsigned long long>(wave, total - first);
-        generate_kernel<<<grid_for(gp.count, ctx, 16), kBlock, 0, st>>>(dcam, gp, ctx->wb.q[0], dc);
-        swap_counts_kernel<<<1, 1, 0, st>>>(dc);
-        launches += 2;
-        waves++;
-        int cur = 0;
-        for (;;) {
-            CU(cudaMemcpyAsync(ctx->h_cnt, dc, 16, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            size_t n = ctx->h_cnt->n_cur;
-            if (n == 0) break;
-            if (n > ctx->wave_rays) return fail(ctx, B2PT_ERR_CUDA, "ray queue overflow (internal error)");
-            Queue &qa = ctx->wb.q[cur], &qb = ctx->wb.q[cur ^ 1];
-            CU(cudaEventRecord(ctx->ev[2], st));
-            if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
-            else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
-            CU(cudaEventRecord(ctx->ev[3], st));
-            launches++; ext_launches++;
-            light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o,
-                                                               ctx->wb.sh_d, ctx->wb.lists, dc, gp.k0, gp.k1);
+    // Path regeneration: every bounce the queue is topped up with new camera rays to `wave` entries, so all kernels work
+    // on full queues until the samples run out; only the end of the call sees the thin tail of deep paths.
+    unsigned long long next_first = 0;
+    size_t n = 0;  // length of the current queue as known to the host
+    int cur = 0;
+    for (;;) {
+        Queue &qa = ctx->wb.q[cur], &qb = ctx->wb.q[cur ^ 1];
+        size_t gen = 0;
+        if (next_first < total && n < wave) {
+            gen = (size_t)std::min<unsigned long long>(wave - n, total - next_first);
+            gp.first = next_first;
+            gp.count = (unsigned)gen;
+            generate_kernel<<<grid_for(gen, ctx, 16), kBlock, 0, st>>>(dcam, gp, qa, &dc->n_cur);
+            next_first += gen;
             launches++;
-            if (S.enable_shadow) {
-                CU(cudaEventRecord(ctx->ev[4], st));
-                if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
-                else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
-                CU(cudaEventRecord(ctx->ev[5], st));
-                launches++; sh_launches++;
-            }
-            {
-                const unsigned g = grid_for(n, ctx, 16);
-                const uint32_t *L = ctx->wb.lists;
-                const size_t cap = qa.cap;
-                terminal_kernel<<<g, kBlock, 0, st>>>(S, qa, L, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
+            waves++;
+        }
+        n += gen * (split ? 3 : 1);  // upper bound (tiles overhang the image edges)
+        if (n == 0) break;
+        if (n > ctx->wave_rays) return fail(ctx, B2PT_ERR_CUDA, "ray queue overflow (internal error)");
+        CU(cudaEventRecord(ctx->ev[2], st));
+        if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+        else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+        CU(cudaEventRecord(ctx->ev[3], st));
+        launches++; ext_launches++;
+        light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o, ctx->wb.sh_d,
+                                                           ctx->wb.lists, dc, gp.k0, gp.k1);
+        launches++;
+        if (S.enable_shadow) {
+            CU(cudaEventRecord(ctx->ev[4], st));
+            if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
+            else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
+            CU(cudaEventRecord(ctx->ev[5], st));
+            launches++; sh_launches++;
+        }
+        {
+            const unsigned g = grid_for(n, ctx, 16);
+            const uint32_t *L = ctx->wb.lists;
+            const size_t cap = qa.cap;
+            terminal_kernel<<<g, kBlock, 0, st>>>(S, qa, L, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
 #define SHADE(T) shade_kernel<T><<<g, kBlock, 0, st>>>(S, qa, qb, L + (size_t)(1 + T) * cap, &dc->n_class[1 + T], ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, dc, sp)
-                SHADE(MAT_SMOOTH_CONDUCTOR); SHADE(MAT_ROUGH_CONDUCTOR); SHADE(MAT_SMOOTH_DIELECTRIC); SHADE(MAT_ROUGH_DIELECTRIC);
+            SHADE(MAT_SMOOTH_CONDUCTOR); SHADE(MAT_ROUGH_CONDUCTOR); SHADE(MAT_SMOOTH_DIELECTRIC); SHADE(MAT_ROUGH_DIELECTRIC);
 #undef SHADE
-                swap_counts_kernel<<<1, 1, 0, st>>>(dc);
-                launches += 6;
-            }
-            cur ^= 1;
-            CU(cudaGetLastError());
-            if (stats) {
-                // the sync at the top of the next iteration completes these events; read them lazily there
-                CU(cudaEventSynchronize(S.enable_shadow ? ctx->ev[5] : ctx->ev[3]));
-                float ms = 0;
-                CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                extend_ms += ms;
-                if (S.enable_shadow) { CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); shadow_ms += ms; }
-            }
+            swap_counts_kernel<<<1, 1, 0, st>>>(dc);
+            launches += 6;
+        }
+        cur ^= 1;
+        CU(cudaMemcpyAsync(ctx->h_cnt, dc, 16, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        n = ctx->h_cnt->n_cur;
+        if (stats) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+            extend_ms += ms;
+            if (S.enable_shadow) { CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); shadow_ms += ms; }
         }
     }
     CU(cudaEventRecord(ctx->ev[1], st));
