@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                 float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
                 NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
                 sh_o[b + k] = make_float4(pn.x, pn.y, pn.z, g.dist);
-                sh_d[b + k] = make_float4(g.ws.x, g.ws.y, g.ws.z, 0.f);
+                sh_d[b + k] = make_float4(g.ws.x, g.ws.y, g.ws.z, __int_as_float(g.prim));
             }
             refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
         }
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
                         float4 o = sh_o[idx], d = sh_d[idx];
                         r = make_ray(xyz(o), xyz(d));
                         dist = o.w;
-                        shadow_begin(S, r, T, dist);
+                        shadow_begin(S, r, T, dist, __float_as_int(d.w));
                         has = true;
                     }
                 }
@@ -496,9 +496,9 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Qu
             const f3 pn = s.p + nrm * kEps;
             const uint32_t sb = sh_base[i];
             for (int k = 0; k < ndir; ++k) {
-                float u0 = stream_next(st), u1 = stream_next(st), u2 = stream_next(st), u3 = stream_next(st);
                 bool lit = !S.enable_shadow || (sb != kNoShadow && vis[sb + k]);
-                if (!lit) continue;
+                if (!lit) { st.dim += 4; continue; }  // the four draws of a rejected sample are skipped, not generated
+                float u0 = stream_next(st), u1 = stream_next(st), u2 = stream_next(st), u3 = stream_next(st);
                 NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)

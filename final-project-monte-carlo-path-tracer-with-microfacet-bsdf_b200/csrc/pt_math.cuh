@@ -195,7 +195,12 @@ PT_HD Ray make_ray(f3 o, f3 d) {
 }
 
 // ---- Bounds3::IntersectP, src/Bounds3.hpp:95-108 ------------------------------------------------------
+PT_HD bool box_hit2(f3 pmin, f3 pmax, const Ray &r, float *tmin_out, float *tmax_out);
 PT_HD bool box_hit(f3 pmin, f3 pmax, const Ray &r, float *tmin_out) {
+    float tmax;
+    return box_hit2(pmin, pmax, r, tmin_out, &tmax);
+}
+PT_HD bool box_hit2(f3 pmin, f3 pmax, const Ray &r, float *tmin_out, float *tmax_out) {
     float t1x = (pmin.x - r.o.x) * r.inv.x, t1y = (pmin.y - r.o.y) * r.inv.y, t1z = (pmin.z - r.o.z) * r.inv.z;
     float t2x = (pmax.x - r.o.x) * r.inv.x, t2y = (pmax.y - r.o.y) * r.inv.y, t2z = (pmax.z - r.o.z) * r.inv.z;
     float mnx = fminf(t1x, t2x), mny = fminf(t1y, t2y), mnz = fminf(t1z, t2z);
@@ -206,6 +211,7 @@ PT_HD bool box_hit(f3 pmin, f3 pmax, const Ray &r, float *tmin_out) {
     float tmin = fmaxf(fmaxf(mnx, mny), mnz);
     float tmax = fminf(fminf(mxx, mxy), mxz);
     *tmin_out = tmin;
+    *tmax_out = tmax;
     return (tmin - kEps <= tmax) && (tmax >= -kEps) && (mnx == mnx);
 }
 
@@ -340,23 +346,22 @@ PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
     float tl = 0.f, tr = 0.f;
     bool hl = box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
     bool hr = box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
-    if (hl && lk != NODE_INTERIOR) {
+    // Leaf children are collected first and tested in ONE loop, so lanes with a left leaf and lanes with a right leaf
+    // run the (long, FP64) primitive test together instead of one after the other.
+    const bool ll = hl && lk != NODE_INTERIOR, rl = hr && rk != NODE_INTERIOR;
+    const int n_leaf = (ll ? 1 : 0) + (rl ? 1 : 0);
+    if (ll) hl = false;
+    if (rl) hr = false;
+#pragma unroll 1
+    for (int k = 0; k < n_leaf; ++k) {
+        const bool left = ll && k == 0;  // slot 0 is the left leaf when there is one
+        const uint32_t prim = left ? la : ra, kind = left ? lk : rk;
+        if ((left ? tl : tr) > T.bound) continue;
         double t;
         if (COUNT) st->prims++;
-        if (prim_hit(S, la, lk, r, &t) && (t < T.h.t || (t == T.h.t && (int)la > T.h.prim))) {
-            T.h.t = t; T.h.prim = (int)la; T.bound = prune_bound(t);
+        if (prim_hit(S, prim, kind, r, &t) && (t < T.h.t || (t == T.h.t && (int)prim > T.h.prim))) {
+            T.h.t = t; T.h.prim = (int)prim; T.bound = prune_bound(t);
         }
-        hl = false;
-    }
-    if (hr && rk != NODE_INTERIOR) {
-        if (!(tr > T.bound)) {
-            double t;
-            if (COUNT) st->prims++;
-            if (prim_hit(S, ra, rk, r, &t) && (t < T.h.t || (t == T.h.t && (int)ra > T.h.prim))) {
-                T.h.t = t; T.h.prim = (int)ra; T.bound = prune_bound(t);
-            }
-        }
-        hr = false;
     }
     if (hl && tl > T.bound) hl = false;
     if (hr && tr > T.bound) hr = false;
@@ -385,23 +390,34 @@ PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
 }
 
 // ---- visibility of a light sample: Scene::directLighting, src/Scene.cpp:72-75 -----------------------------
-// visible <=> the CLOSEST hit exists and |distance - dist| < EPSILON (compared in double).  Equivalent
-// without finding the closest hit: no hit with t <= dist - EPSILON exists (early exit when one is
-// found) and some hit lies inside the window; subtrees entered beyond the window are skipped.
+// visible <=> the CLOSEST hit exists and |distance - dist| < EPSILON (compared in double)
+//         <=> (W) some hit lies inside the window  and  (O) no hit has t < dist outside the window.
+// The walk answers (W) first and cheaply: if the sampled light triangle itself is hit inside the window (the usual
+// case when the sample is accepted) W holds at once; otherwise only boxes that overlap the window in t can hold a
+// witness, which is a handful of nodes around the light — and when W fails the sample is rejected without ever
+// looking for occluders (at scene scale ~1e3 the 1e-4 window is below float resolution, so most unoccluded samples
+// of the chess scene end here).  Only when W holds is (O) searched, near child first, stopping at the first occluder.
 struct ShadowTrav {
     const float4 *nodes;
-    bool in_window, visible;
-    float bound;
+    bool visible;
+    int phase;  // 1: window search (W), 2: occluder search (O)
+    float lo, hi;
     uint32_t pair;
     int sp;
     uint32_t stk[kStackSize];
 };
-PT_HD void shadow_begin(const SceneView &S, const Ray &r, ShadowTrav &T, float dist) {
+PT_HD void shadow_begin(const SceneView &S, const Ray &r, ShadowTrav &T, float dist, int light_prim = -1) {
     T.nodes = ray_needs_reference_tree(r) ? S.nodes_ref : S.nodes;
-    T.in_window = false; T.visible = false;
-    T.bound = dist + (4e-3f + 1e-5f * dist);
+    T.visible = false;
+    const float m = 4e-3f + 1e-5f * dist;
+    T.lo = dist - m; T.hi = dist + m;
     T.sp = 0;
     T.pair = 0;
+    T.phase = 1;
+    if (light_prim >= 0) {
+        double t;
+        if (prim_hit(S, (uint32_t)light_prim, PT_LDG(S.prim_kind + light_prim), r, &t) && fabs(t - (double)dist) < (double)kEps) T.phase = 2;
+    }
 }
 // Returns false when the decision is known (T.visible).
 template <bool COUNT>
@@ -411,27 +427,35 @@ PT_HD bool shadow_step(const SceneView &S, const Ray &r, float dist, ShadowTrav 
     float4 l0 = PT_LDG4(p), l1 = PT_LDG4(p + 1), r0 = PT_LDG4(p + 2), r1 = PT_LDG4(p + 3);
     if (COUNT) st->nodes += 2;
     uint32_t lk = f2u(l1.w), rk = f2u(r1.w), la = f2u(l0.w), ra = f2u(r0.w);
-    float tl = 0.f, tr = 0.f;
-    bool hl = box_hit(xyz(l0), xyz(l1), r, &tl) && !(tl > T.bound);
-    bool hr = box_hit(xyz(r0), xyz(r1), r, &tr) && !(tr > T.bound);
-    if (hl && lk != NODE_INTERIOR) {
+    float tl = 0.f, tr = 0.f, xl = 0.f, xr = 0.f;
+    bool hl = box_hit2(xyz(l0), xyz(l1), r, &tl, &xl) && !(tl > T.hi);
+    bool hr = box_hit2(xyz(r0), xyz(r1), r, &tr, &xr) && !(tr > T.hi);
+    if (T.phase == 1) {  // only boxes that overlap the window in t can hold a witness
+        hl = hl && !(xl < T.lo);
+        hr = hr && !(xr < T.lo);
+    }
+    const bool ll = hl && lk != NODE_INTERIOR, rl = hr && rk != NODE_INTERIOR;
+    const int n_leaf = (ll ? 1 : 0) + (rl ? 1 : 0);
+#pragma unroll 1
+    for (int k = 0; k < n_leaf; ++k) {  // one loop: left-leaf and right-leaf lanes test together
+        const bool left = ll && k == 0;
         double t;
         if (COUNT) st->prims++;
-        if (prim_hit(S, la, lk, r, &t)) {
-            if (fabs(t - dd) < eps) T.in_window = true;
-            else if (t < dd) { T.visible = false; return false; }  // a closer hit outside the window: the closest hit fails the test
+        if (prim_hit(S, left ? la : ra, left ? lk : rk, r, &t)) {
+            const bool inside = fabs(t - dd) < eps;
+            if (T.phase == 1) {
+                if (inside) {  // W holds: restart as the occluder search
+                    T.phase = 2; T.sp = 0; T.pair = 0;
+                    return true;
+                }
+            } else if (!inside && t < dd) {  // a closer hit outside the window: the closest hit fails the test
+                T.visible = false;
+                return false;
+            }
         }
-        hl = false;
     }
-    if (hr && rk != NODE_INTERIOR) {
-        double t;
-        if (COUNT) st->prims++;
-        if (prim_hit(S, ra, rk, r, &t)) {
-            if (fabs(t - dd) < eps) T.in_window = true;
-            else if (t < dd) { T.visible = false; return false; }
-        }
-        hr = false;
-    }
+    hl = hl && lk == NODE_INTERIOR;
+    hr = hr && rk == NODE_INTERIOR;
     if (hl && hr) {
         bool left_near = !(tr < tl);
         T.stk[T.sp++] = left_near ? ra : la;
@@ -440,14 +464,14 @@ PT_HD bool shadow_step(const SceneView &S, const Ray &r, float dist, ShadowTrav 
     }
     if (hl) { T.pair = la; return true; }
     if (hr) { T.pair = ra; return true; }
-    if (T.sp == 0) { T.visible = T.in_window; return false; }
+    if (T.sp == 0) { T.visible = (T.phase == 2); return false; }
     T.pair = T.stk[--T.sp];
     return true;
 }
 template <bool COUNT>
-PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st) {
+PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st, int light_prim = -1) {
     ShadowTrav T;
-    shadow_begin(S, r, T, dist);
+    shadow_begin(S, r, T, dist, light_prim);
     while (shadow_step<COUNT>(S, r, dist, T, st)) {}
     return T.visible;
 }
@@ -692,10 +716,11 @@ PT_HD f3 env_lookup(const SceneView &S, f3 dir) {
 struct LightSample {
     f3 p, n, emit;
     float pdf;
+    int prim;  // the sampled light triangle
 };
 PT_HD LightSample sample_light(const SceneView &S, float u0, float u1, float u2, float u3) {
     LightSample ls;
-    ls.p = mk3(0, 0, 0); ls.n = mk3(0, 0, 0); ls.emit = mk3(0, 0, 0); ls.pdf = 1.f;
+    ls.p = mk3(0, 0, 0); ls.n = mk3(0, 0, 0); ls.emit = mk3(0, 0, 0); ls.pdf = 1.f; ls.prim = -1;
     float sum = 0;
     for (int i = 0; i < S.n_lights; ++i) sum += S.light_area[i];
     float p = u0 * sum;
@@ -713,6 +738,7 @@ PT_HD LightSample sample_light(const SceneView &S, float u0, float u1, float u2,
                 else { q = q - la; node = S.ln_right[node]; }
             }
             int prim = S.ln_prim[node];
+            ls.prim = prim;
             f3 v0 = xyz(PT_LDG4(S.v0 + prim));
             const float *w = S.v1v2 + 6 * (size_t)prim;
             f3 v1 = mk3(w[0], w[1], w[2]), v2 = mk3(w[3], w[4], w[5]);
@@ -768,6 +794,7 @@ PT_HD void camera_ray(const Camera &cam, int i, int j, Stream &rs, f3 *pos, f3 *
 struct NeeGeom {
     f3 ws, n_light, emit;
     float dist, pdf;
+    int prim;
 };
 PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u2, float u3) {
     LightSample ls = sample_light(S, u0, u1, u2, u3);
@@ -775,7 +802,7 @@ PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u
     f3 d = ls.p - p;
     g.ws = normalized(d);
     g.dist = norm(d);
-    g.n_light = ls.n; g.emit = ls.emit; g.pdf = ls.pdf;
+    g.n_light = ls.n; g.emit = ls.emit; g.pdf = ls.pdf; g.prim = ls.prim;
     return g;
 }
 PT_HD float nee_term(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, float u, float v, bool is_reflect, int n_dir) {

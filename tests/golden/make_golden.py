@@ -52,7 +52,7 @@ def bsdf():
 def scene_vectors(name, sc, env):
     ref = S.Ref(sc, env)
     cam = sc.camera
-    o, d, (p, ws, dist) = scenes.ray_batch(ref, sc, n_pixels=900, samples=1, seed=105)
+    o, d, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=900, samples=1, seed=105)
     prim, t, co, nn, uv = ref.intersect(o, d)
     sprim, st, *_ = ref.intersect(p, ws)
     visible = ((sprim >= 0) & (np.abs(st - dist.astype(np.float64)) < np.float64(np.float32(1e-4)))).astype(np.int32)

@@ -86,6 +86,15 @@ void hc_shadow(void *h, const float *o, const float *d, const float *dist, long 
         visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st) ? 1 : 0;
     }
 }
+// as the render path calls it: with the id of the sampled light triangle
+void hc_shadow_prim(void *h, const float *o, const float *d, const float *dist, const int *light_prim, long n, int *visible) {
+    const SceneView &S = ((HcScene *)h)->view;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st, light_prim[i]) ? 1 : 0;
+    }
+}
 void hc_surface(void *h, const float *o, const float *d, long n, float *coords, float *normal, float *uv) {
     const SceneView &S = ((HcScene *)h)->view;
     for (long i = 0; i < n; ++i) {
@@ -161,6 +170,10 @@ void hc_sample_light(void *h, const float *u4, long n, float *coords, float *nor
         emit[3 * i] = ls.emit.x; emit[3 * i + 1] = ls.emit.y; emit[3 * i + 2] = ls.emit.z;
         pdf[i] = ls.pdf;
     }
+}
+void hc_sample_light_prim(void *h, const float *u4, long n, int *prim) {
+    const SceneView &S = ((HcScene *)h)->view;
+    for (long i = 0; i < n; ++i) prim[i] = sample_light(S, u4[4 * i], u4[4 * i + 1], u4[4 * i + 2], u4[4 * i + 3]).prim;
 }
 void hc_camera_rays(const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count, unsigned long long seed,
                     float *o, float *d) {

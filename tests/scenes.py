@@ -77,4 +77,4 @@ def ray_batch(ref: "S.Ref", scene, n_pixels=600, samples=2, seed=1):
     ws = (w / dist[:, None]).astype(np.float32)
     rays_o = np.concatenate([o, p, p]).astype(np.float32)
     rays_d = np.concatenate([d, v, ws]).astype(np.float32)
-    return rays_o, rays_d, (p, ws, dist)
+    return rays_o, rays_d, (p, ws, dist, u4)

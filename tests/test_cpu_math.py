@@ -102,12 +102,15 @@ def test_textured_uv(world):
 
 def test_shadow_decision(world):
     name, sc, ref, hc = world
-    _, _, (p, ws, dist) = scenes.ray_batch(ref, sc, n_pixels=1500, samples=2, seed=4)
+    _, _, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=1500, samples=2, seed=4)
     prim_r, t_r, *_ = ref.intersect(p, ws)
     want = ((prim_r >= 0) & (np.abs(t_r - dist.astype(np.float64)) < np.float64(np.float32(1e-4)))).astype(np.int32)
     got = hc.shadow(p, ws, dist)
     assert np.array_equal(got, want), f"{name}: {(got != want).sum()} of {len(want)} visibility decisions differ"
     assert 0.01 < want.mean() < 0.99
+    # the render path also passes the sampled light triangle (tested first): same decisions
+    got2 = hc.shadow_with_light_prim(p, ws, dist, hc.sample_light_prim(u4))
+    assert np.array_equal(got2, want)
 
 
 def test_bsdf_parity():

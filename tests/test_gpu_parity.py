@@ -98,7 +98,7 @@ def test_degenerate_rays_take_the_reference_tree(ctx, world):
 
 def test_shadow_decision(ctx, world):
     name, sc, ref = world
-    _, _, (p, ws, dist) = scenes.ray_batch(ref, sc, n_pixels=3000, samples=2, seed=4)
+    _, _, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=3000, samples=2, seed=4)
     prim_r, t_r, *_ = ref.intersect(p, ws)
     want = ((prim_r >= 0) & (np.abs(t_r - dist.astype(np.float64)) < np.float64(np.float32(1e-4)))).astype(np.int32)
     got = ctx.shadow(p, ws, dist)
