@@ -471,8 +471,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Qu
             Hit h;
             h.prim = hit_prim[i]; h.t = (double)hit_t[i];
             const Surface s = surface_at(S, rs.r, h);
-            Material m = S.mats[s.mat];
-            m.type = TYPE;  // known at compile time: folds the type switches of Material.hpp
+            const Material &m = S.mats[s.mat];  // read in place: the material functions are out-of-line calls
             const f3 wo = -rs.r.d;
             verts += (unsigned)rs.nch;
             if (depth > maxd) maxd = depth;
@@ -495,15 +494,26 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneView S, Queue qi, Qu
             const bool inner = dot(wo, nrm) < 0;
             const f3 pn = s.p + nrm * kEps;
             const uint32_t sb = sh_base[i];
-            for (int k = 0; k < ndir; ++k) {
-                bool lit = !S.enable_shadow || (sb != kNoShadow && vis[sb + k]);
-                if (!lit) { st.dim += 4; continue; }  // the four draws of a rejected sample are skipped, not generated
-                float u0 = stream_next(st), u1 = stream_next(st), u2 = stream_next(st), u3 = stream_next(st);
-                NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
+            // Only the accepted samples are evaluated, in sample order (the order l_dir accumulates in, Scene.cpp:76-79);
+            // looping over the set bits keeps lanes with any accepted sample together.
+            const uint32_t dim_nee = st.dim;
+            for (int k0 = 0; k0 < ndir; k0 += 32) {
+                const int kn = min(32, ndir - k0);
+                uint32_t litmask = 0;
+                for (int k = 0; k < kn; ++k)
+                    if (!S.enable_shadow || (sb != kNoShadow && vis[sb + k0 + k])) litmask |= 1u << k;
+                while (litmask) {
+                    const int k = k0 + __ffs(litmask) - 1;
+                    litmask &= litmask - 1;
+                    st.dim = dim_nee + 4u * (uint32_t)k;
+                    float u0 = stream_next(st), u1 = stream_next(st), u2 = stream_next(st), u3 = stream_next(st);
+                    NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    if (j < rs.nch) ldir[j] += nee_term(m, g, wo, nrm, rs.ch[j], s.u, s.v, !inner, ndir);
+                    for (int j = 0; j < 3; ++j)
+                        if (j < rs.nch) ldir[j] += nee_term(m, g, wo, nrm, rs.ch[j], s.u, s.v, !inner, ndir);
+                }
             }
+            st.dim = dim_nee + 4u * (uint32_t)ndir;
 #pragma unroll
             for (int j = 0; j < 3; ++j) ldir[j] = inner ? (float)((1. - (double)kr[j]) * (double)ldir[j]) : kr[j] * ldir[j];
 

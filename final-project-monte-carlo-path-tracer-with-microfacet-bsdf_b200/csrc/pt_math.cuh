@@ -18,8 +18,12 @@
 
 #if defined(__CUDACC__)
 #define PT_HD __host__ __device__ __forceinline__
+// Out-of-line on the device: the shading kernels call these many times (per wavelength, per light sample); inlining every
+// call made them several thousand instructions long and instruction-fetch bound (ncu: stall_no_instruction).
+#define PT_HD_NI __host__ __device__ __noinline__
 #else
 #define PT_HD inline
+#define PT_HD_NI inline
 #endif
 #if defined(__CUDA_ARCH__)
 #define PT_LDG4(p) __ldg(reinterpret_cast<const float4 *>(p))
@@ -75,7 +79,7 @@ PT_HD float clamp_ref(float lo, float hi, float v) {
 
 // ---- sample streams (replace std::mt19937 + random_device, src/global.hpp:42-53) ---------------
 // Philox4x32-10; stream (pixel, sample, tag); draw `dim` = word dim&3 of block dim>>2.
-PT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+PT_HD_NI uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
@@ -87,7 +91,7 @@ PT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
 }
 enum { STREAM_PATH = 0, STREAM_CAMERA = 1 };
 struct Stream {
@@ -106,7 +110,8 @@ PT_HD Stream stream_open(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t samp
 PT_HD float stream_next(Stream &s) {
     uint32_t b = s.dim >> 2;
     if (b != s.blk) {
-        philox4x32_10(s.pixel, s.sample, b, s.tag, s.k0, s.k1, s.w);
+        uint4 w = philox4x32_10(s.pixel, s.sample, b, s.tag, s.k0, s.k1);
+        s.w[0] = w.x; s.w[1] = w.y; s.w[2] = w.z; s.w[3] = w.w;
         s.blk = b;
     }
     uint32_t i = s.dim & 3u;
@@ -533,7 +538,7 @@ PT_HD float fresnel_schlick(const Material &m, float cos_theta, float u, float v
     float c2 = invc * invc;
     return f + (1.f - f) * c2 * c2 * invc;
 }
-PT_HD float mat_fresnel(const Material &m, f3 I, f3 N, int c) {  // fresnel, :198-226
+PT_HD_NI float mat_fresnel(const Material &m, f3 I, f3 N, int c) {  // fresnel, :198-226
     if (mat_is_conductor(m)) return 1;
     float cosi = clamp_ref(-1, 1, dot(I, N));
     float etai = 1, etat = mat_ior(m, c);
@@ -546,7 +551,7 @@ PT_HD float mat_fresnel(const Material &m, f3 I, f3 N, int c) {  // fresnel, :19
     float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
     return (Rs * Rs + Rp * Rp) / 2;
 }
-PT_HD f3 mat_refract(const Material &m, f3 I, f3 N, int c) {  // refract, :227-242
+PT_HD_NI f3 mat_refract(const Material &m, f3 I, f3 N, int c) {  // refract, :227-242
     float cosi = clamp_ref(-1, 1, dot(I, N));
     float etai = 1, etat = mat_ior(m, c);
     f3 n = N;
@@ -578,7 +583,7 @@ PT_HD float g1_ggx(f3 v, f3 n, float alpha) {  // G1_SmithGGX, :38-69
 PT_HD float g_ggx(f3 wi, f3 wo, f3 n, float alpha) { return g1_ggx(wi, n, alpha) * g1_ggx(wo, n, alpha); }
 
 // tanToWorld + ImportanceSampleGGX, :95-130.  xi_x / xi_y are Vector2f Xi's components.
-PT_HD f3 ggx_sample(float xi_x, float xi_y, float alpha, f3 n) {
+PT_HD_NI f3 ggx_sample(float xi_x, float xi_y, float alpha, f3 n) {
     float phi = 2.0f * kPi * xi_x;
     float cosTheta = sqrtf((1.0f - xi_y) / (1.0f + (alpha * alpha - 1.0f) * xi_y));
     float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
@@ -604,7 +609,7 @@ PT_HD f3 ggx_sample_draws(float first_draw, float second_draw, float alpha, f3 n
     return ggx_sample(second_draw, first_draw, alpha, n);
 }
 
-PT_HD float mat_pdf(const Material &m, f3 wi, f3 wo, f3 N, int c, bool is_reflect) {  // pdf, :285-328
+PT_HD_NI float mat_pdf(const Material &m, f3 wi, f3 wo, f3 N, int c, bool is_reflect) {  // pdf, :285-328
     if (mat_is_rough(m)) {
         f3 h;
         float jac;
@@ -634,7 +639,7 @@ PT_HD float mat_pdf(const Material &m, f3 wi, f3 wo, f3 N, int c, bool is_reflec
     return (fabsf(dot(h, N)) > 1 - kEps) ? 1.0f : 0.0f;
 }
 
-PT_HD float mat_eval(const Material &m, f3 wi, f3 wo, f3 N, int c, float u, float v, bool is_reflect) {  // eval, :330-408
+PT_HD_NI float mat_eval(const Material &m, f3 wi, f3 wo, f3 N, int c, float u, float v, bool is_reflect) {  // eval, :330-408
     if (mat_is_rough(m)) {
         if (is_reflect) {
             if (dot(wi, N) * dot(wo, N) <= 0) return 0.f;
