@@ -50,7 +50,7 @@ thread_local std::string g_create_error;
 
 // ---- device counters ---------------------------------------------------------------------------
 struct Counters {
-    unsigned int n_cur, n_next, n_shadow, pad;
+    unsigned int n_cur, n_next, n_shadow, n_vis;  // n_shadow: shadow rays queued for traversal; n_vis: visibility slots handed out
     unsigned int n_class[8];
     unsigned int fetch_extend, fetch_shadow;  // dynamic-fetch cursors of the traversal kernels
     unsigned int pad1[2];
@@ -75,8 +75,9 @@ struct WaveBufs {
     float *hit_t;
     uint32_t *sh_base;
     uint32_t *lists;  // [kClasses][cap] ray indices by class
+    float4 *cand_o, *cand_d;  // every light sample: origin.xyz | dist, direction.xyz | light-tree leaf; indexed by visibility slot
     float4 *sh_o;  // origin.xyz, w = dist
-    float4 *sh_d;  // direction.xyz
+    float4 *sh_d;  // direction.xyz, w = visibility slot | phase bit
     unsigned char *vis;
 };
 
@@ -259,8 +260,8 @@ __device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int 
 // Every queued ray is filed under one of five classes — terminal (miss or emitter) or the MaterialType of
 // the surface it hit — so that the shading kernels run with warps whose lanes take the same code path.
 __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
-                                                       const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ sh_o,
-                                                       float4 *__restrict__ sh_d, uint32_t *__restrict__ lists, Counters *cnt, uint32_t k0, uint32_t k1) {
+                                                       const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ cand_o,
+                                                       float4 *__restrict__ cand_d, uint32_t *__restrict__ lists, Counters *cnt, uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
@@ -298,27 +299,63 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
             base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
             if (cls == c) lists[(size_t)c * q.cap + base + (unsigned)__popc(b & lanemask_lt())] = i;
         }
+        // visibility slots: ndir per surviving vertex
         unsigned ballot = __ballot_sync(0xffffffffu, want);
         unsigned base = 0;
-        if (lane == 0 && ballot) base = atomicAdd(&cnt->n_shadow, (unsigned)__popc(ballot) * ndir);
+        if (lane == 0 && ballot) base = atomicAdd(&cnt->n_vis, (unsigned)__popc(ballot) * ndir);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (i < n) sh_base[i] = want ? base + (unsigned)__popc(ballot & lanemask_lt()) * ndir : kNoShadow;
+        const unsigned vb = base + (unsigned)__popc(ballot & lanemask_lt()) * ndir;
+        if (i < n) sh_base[i] = want ? vb : kNoShadow;
         if (want) {
-            unsigned b = base + (unsigned)__popc(ballot & lanemask_lt()) * ndir;
             f3 pn = p + nn * kEps;  // inter.coords += n * EPSILON, Scene.cpp:114
             uint32_t dim = (info & INFO_DIM_MASK) + (mat_is_rough(S.mats[mat]) ? 2u : 0u);
             Stream rs = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), STREAM_PATH, dim);
             for (unsigned k = 0; k < ndir; ++k) {
                 float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
                 NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
-                sh_o[b + k] = make_float4(pn.x, pn.y, pn.z, g.dist);
-                sh_d[b + k] = make_float4(g.ws.x, g.ws.y, g.ws.z, __int_as_float(g.prim));
+                cand_o[vb + k] = make_float4(pn.x, pn.y, pn.z, g.dist);
+                cand_d[vb + k] = make_float4(g.ws.x, g.ws.y, g.ws.z, __int_as_float(g.lnode));
             }
             refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
         }
     }
     refs = warp_sum(refs);
     if (lane == 0 && refs) atomicAdd(&cnt->rays_reference, refs);
+}
+
+// ---- window: the "some hit lies within EPSILON of dist" half of Scene.cpp:74-75, one lane per light sample -------------------
+// Tested against the light neighbourhood table (no traversal).  A sample whose window holds no hit is rejected here and
+// never becomes a shadow ray; the others are compacted into the shadow queue for the occluder search.
+__global__ void __launch_bounds__(kBlock) window_kernel(SceneView S, const float4 *__restrict__ cand_o, const float4 *__restrict__ cand_d,
+                                                        const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis,
+                                                        float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt) {
+    const unsigned n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
+    for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
+        const unsigned i = it + threadIdx.x;
+        bool queue = false;
+        int w = 0;
+        float4 o, d;
+        if (i < n) {
+            o = cand_o[i]; d = cand_d[i];
+            w = window_witness(S, make_ray(xyz(o), xyz(d)), o.w, __float_as_int(d.w));
+            if (w == 0) vis[i] = 0;
+            else queue = true;
+        }
+        unsigned qb = __ballot_sync(0xffffffffu, queue);
+        if (!qb) continue;
+        unsigned qbase = 0;
+        const int leader = __ffs(qb) - 1;
+        if ((int)lane == leader) qbase = atomicAdd(&cnt->n_shadow, (unsigned)__popc(qb));
+        qbase = __shfl_sync(0xffffffffu, qbase, leader);
+        if (queue) {
+            unsigned q = qbase + (unsigned)__popc(qb & lanemask_lt());
+            sh_o[q] = o;
+            // w == 1: a witness exists, only occluders are searched (phase 2); w < 0: no table entry, search the window first
+            sh_d[q] = make_float4(d.x, d.y, d.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
+        }
+    }
 }
 
 // ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
@@ -330,7 +367,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
     const unsigned lane = threadIdx.x & 31u;
     TravStats st{0, 0};
     bool has = false, exhausted = false;
-    unsigned idx = 0;
+    unsigned idx = 0, slot = 0;  // slot: where the decision goes (sh_base[vertex] + sample)
     float dist = 0.f;
     Ray r;
     ShadowTrav T;
@@ -350,7 +387,9 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
                         float4 o = sh_o[idx], d = sh_d[idx];
                         r = make_ray(xyz(o), xyz(d));
                         dist = o.w;
-                        shadow_begin(S, r, T, dist, __float_as_int(d.w));
+                        const uint32_t tag = __float_as_uint(d.w);
+                        shadow_begin(S, r, T, dist, (tag & 0x80000000u) ? 1 : 2);
+                        slot = tag & 0x7FFFFFFFu;
                         has = true;
                     }
                 }
@@ -361,7 +400,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneView S, const float
         if (!act) break;
         do {
             if (has && !shadow_step<COUNT>(S, r, dist, T, &st)) {
-                vis[idx] = T.visible ? 1 : 0;
+                vis[slot] = T.visible ? 1 : 0;
                 has = false;
             }
             act = __ballot_sync(0xffffffffu, has);
@@ -612,6 +651,7 @@ __global__ void swap_counts_kernel(Counters *cnt) {
     cnt->n_cur = cnt->n_next;
     cnt->n_next = 0;
     cnt->n_shadow = 0;
+    cnt->n_vis = 0;
     for (int c = 0; c < kClasses; ++c) cnt->n_class[c] = 0;
     cnt->fetch_extend = 0;
     cnt->fetch_shadow = 0;
@@ -814,7 +854,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t per_queue = al(rays * 16) * 2 + al(rays * 4) * 2 + al(rays * 16 * 6);
     size_t shadows = rays * (size_t)ndir;
-    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows);
+    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 4 + al(shadows);
     release(ctx->wave_mem);
     ctx->wave_rays = 0;
     int r = ensure(ctx, ctx->wave_mem, total);
@@ -832,6 +872,8 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     ctx->wb.hit_t = (float *)take(rays * 4);
     ctx->wb.sh_base = (uint32_t *)take(rays * 4);
     ctx->wb.lists = (uint32_t *)take(rays * 4 * kClasses);
+    ctx->wb.cand_o = (float4 *)take(shadows * 16);
+    ctx->wb.cand_d = (float4 *)take(shadows * 16);
     ctx->wb.sh_o = (float4 *)take(shadows * 16);
     ctx->wb.sh_d = (float4 *)take(shadows * 16);
     ctx->wb.vis = (unsigned char *)take(shadows);
@@ -910,10 +952,13 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
         CU(cudaEventRecord(ctx->ev[3], st));
         launches++; ext_launches++;
-        light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.sh_o, ctx->wb.sh_d,
+        light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.cand_o, ctx->wb.cand_d,
                                                            ctx->wb.lists, dc, gp.k0, gp.k1);
         launches++;
         if (S.enable_shadow) {
+            window_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.cand_o, ctx->wb.cand_d, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o,
+                                                                                   ctx->wb.sh_d, dc);
+            launches++;
             CU(cudaEventRecord(ctx->ev[4], st));
             if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
             else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
@@ -1078,7 +1123,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     free_scene(ctx);
     PackedScene packed;
     pack_scene(d, packed);
-    ctx->scene_bufs.resize(19);
+    ctx->scene_bufs.resize(22);
     auto up = [&](int slot, const void *src, size_t bytes) -> void * {
         if (upload(ctx, ctx->scene_bufs[slot], src, bytes)) return nullptr;
         return ctx->scene_bufs[slot].p;
@@ -1105,6 +1150,9 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(ln_left, const int *, 14, d->light_node_left, 4 * (size_t)d->n_light_nodes);
     UP(ln_right, const int *, 15, d->light_node_right, 4 * (size_t)d->n_light_nodes);
     UP(ln_prim, const int *, 16, d->light_node_prim, 4 * (size_t)d->n_light_nodes);
+    UP(lt_entries, const float4 *, 19, packed.lt_entries.data(), 16 * packed.lt_entries.size());
+    UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
+    UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;

@@ -178,6 +178,8 @@ struct SceneView {
     const uint32_t *light_root, *light_mat;
     const float *ln_area;
     const int *ln_left, *ln_right, *ln_prim;
+    const float4 *lt_entries;  // light neighbourhood table (pt_pack.hpp): 2 float4 per entry
+    const int *lt_off, *lt_cnt;
     int use_env, env_w, env_h;
     const float4 *env;      // texels as float4 (rgb, 0)
     unsigned long long env_tex;  // the same texels as a point-sampled CUDA texture object (device only; 0 = use `env`)
@@ -411,18 +413,33 @@ struct ShadowTrav {
     int sp;
     uint32_t stk[kStackSize];
 };
-PT_HD void shadow_begin(const SceneView &S, const Ray &r, ShadowTrav &T, float dist, int light_prim = -1) {
+// (W) without a traversal: a witness lies within EPSILON of the sampled point, so it is the sampled triangle or one of the
+// few primitives listed next to it in the light neighbourhood table.  Each candidate's own leaf box is tested first, as
+// the reference does.  Returns 1 = witness found, 0 = none exists (the sample is rejected), -1 = unknown (no table entry:
+// search the window by traversal).
+PT_HD int window_witness(const SceneView &S, const Ray &r, float dist, int lnode) {
+    if (lnode < 0) return -1;
+    const int cnt = PT_LDG(S.lt_cnt + lnode);
+    if (cnt <= 0) return -1;
+    const float4 *e = S.lt_entries + 2 * (size_t)PT_LDG(S.lt_off + lnode);
+    const double dd = (double)dist;
+    for (int i = 0; i < cnt; ++i) {
+        float4 a = PT_LDG4(e + 2 * i), b = PT_LDG4(e + 2 * i + 1);
+        float tmin;
+        if (!box_hit(xyz(a), xyz(b), r, &tmin)) continue;
+        double t;
+        if (prim_hit(S, f2u(a.w), f2u(b.w), r, &t) && fabs(t - dd) < (double)kEps) return 1;
+    }
+    return 0;
+}
+PT_HD void shadow_begin(const SceneView &S, const Ray &r, ShadowTrav &T, float dist, int phase = 1) {
     T.nodes = ray_needs_reference_tree(r) ? S.nodes_ref : S.nodes;
     T.visible = false;
     const float m = 4e-3f + 1e-5f * dist;
     T.lo = dist - m; T.hi = dist + m;
     T.sp = 0;
     T.pair = 0;
-    T.phase = 1;
-    if (light_prim >= 0) {
-        double t;
-        if (prim_hit(S, (uint32_t)light_prim, PT_LDG(S.prim_kind + light_prim), r, &t) && fabs(t - (double)dist) < (double)kEps) T.phase = 2;
-    }
+    T.phase = phase;
 }
 // Returns false when the decision is known (T.visible).
 template <bool COUNT>
@@ -474,9 +491,11 @@ PT_HD bool shadow_step(const SceneView &S, const Ray &r, float dist, ShadowTrav 
     return true;
 }
 template <bool COUNT>
-PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st, int light_prim = -1) {
+PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats *st, int lnode = -1) {
+    int w = window_witness(S, r, dist, lnode);
+    if (w == 0) return false;
     ShadowTrav T;
-    shadow_begin(S, r, T, dist, light_prim);
+    shadow_begin(S, r, T, dist, w == 1 ? 2 : 1);
     while (shadow_step<COUNT>(S, r, dist, T, st)) {}
     return T.visible;
 }
@@ -722,10 +741,11 @@ struct LightSample {
     f3 p, n, emit;
     float pdf;
     int prim;  // the sampled light triangle
+    int node;  // its leaf in the light tree
 };
 PT_HD LightSample sample_light(const SceneView &S, float u0, float u1, float u2, float u3) {
     LightSample ls;
-    ls.p = mk3(0, 0, 0); ls.n = mk3(0, 0, 0); ls.emit = mk3(0, 0, 0); ls.pdf = 1.f; ls.prim = -1;
+    ls.p = mk3(0, 0, 0); ls.n = mk3(0, 0, 0); ls.emit = mk3(0, 0, 0); ls.pdf = 1.f; ls.prim = -1; ls.node = -1;
     float sum = 0;
     for (int i = 0; i < S.n_lights; ++i) sum += S.light_area[i];
     float p = u0 * sum;
@@ -744,6 +764,7 @@ PT_HD LightSample sample_light(const SceneView &S, float u0, float u1, float u2,
             }
             int prim = S.ln_prim[node];
             ls.prim = prim;
+            ls.node = node;
             f3 v0 = xyz(PT_LDG4(S.v0 + prim));
             const float *w = S.v1v2 + 6 * (size_t)prim;
             f3 v1 = mk3(w[0], w[1], w[2]), v2 = mk3(w[3], w[4], w[5]);
@@ -799,7 +820,7 @@ PT_HD void camera_ray(const Camera &cam, int i, int j, Stream &rs, f3 *pos, f3 *
 struct NeeGeom {
     f3 ws, n_light, emit;
     float dist, pdf;
-    int prim;
+    int lnode;  // leaf of the light tree the sample came from
 };
 PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u2, float u3) {
     LightSample ls = sample_light(S, u0, u1, u2, u3);
@@ -807,7 +828,7 @@ PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u
     f3 d = ls.p - p;
     g.ws = normalized(d);
     g.dist = norm(d);
-    g.n_light = ls.n; g.emit = ls.emit; g.pdf = ls.pdf; g.prim = ls.prim;
+    g.n_light = ls.n; g.emit = ls.emit; g.pdf = ls.pdf; g.lnode = ls.node;
     return g;
 }
 PT_HD float nee_term(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, float u, float v, bool is_reflect, int n_dir) {

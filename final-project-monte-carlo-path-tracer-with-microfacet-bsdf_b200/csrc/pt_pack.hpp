@@ -19,7 +19,13 @@ struct PackedScene {
     std::vector<b2pt_node> nodes_ref;   // the reference's topology, EMPTY boxes rewritten to NaN
     std::vector<b2pt_node> nodes_fast;  // binned-SAH tree over the same leaves (pt_build.hpp)
     int fast_depth = 0;
+    // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
+    // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
+    // Entry = (bmin, prim id) (bmax, kind): the primitive's own reference leaf box, tested before the primitive.
+    std::vector<float4> lt_entries;
+    std::vector<int> lt_off, lt_cnt;  // cnt < 0: too many neighbours, the window is searched by traversal instead
 };
+constexpr int kMaxLightNeighbours = 12;
 
 inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
     if (!d) { err = "scene is NULL"; return false; }
@@ -64,6 +70,53 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
         if (b.max_depth + 2 < kStackSize) { out.nodes_fast.swap(b.out); out.fast_depth = b.max_depth; }
     }
     if (out.nodes_fast.empty()) { out.nodes_fast = out.nodes_ref; out.fast_depth = (int)d->max_depth; }
+    {
+        // leaf boxes by primitive id
+        std::vector<BuildBox> pb(d->n_prims, box_empty_b());
+        BuildBox all = box_empty_b();
+        for (uint32_t i = 0; i < d->n_nodes; ++i) {
+            const b2pt_node &n = d->nodes[i];
+            if (n.kind != B2PT_NODE_TRIANGLE && n.kind != B2PT_NODE_SPHERE) continue;
+            for (int k = 0; k < 3; ++k) { pb[n.a].mn[k] = n.bmin[k]; pb[n.a].mx[k] = n.bmax[k]; }
+            box_grow(all, pb[n.a]);
+        }
+        float diag = 0.f;
+        for (int k = 0; k < 3; ++k) diag += (all.mx[k] - all.mn[k]) * (all.mx[k] - all.mn[k]);
+        // A witness hit lies within EPSILON (+ float rounding of dist, ws and the hit point, ~1e-6 of the scene size) of the
+        // sampled point; delta is three orders of magnitude above that.
+        const float delta = 1e-3f * std::sqrt(diag) + 0.01f;
+        out.lt_entries.clear();
+        out.lt_off.assign(d->n_light_nodes, 0);
+        out.lt_cnt.assign(d->n_light_nodes, 0);
+        auto entry = [&](uint32_t prim) {
+            float4 a = make_float4(pb[prim].mn[0], pb[prim].mn[1], pb[prim].mn[2], 0.f), b = make_float4(pb[prim].mx[0], pb[prim].mx[1], pb[prim].mx[2], 0.f);
+            uint32_t kind = d->prim_kind[prim];
+            std::memcpy(&a.w, &prim, 4);
+            std::memcpy(&b.w, &kind, 4);
+            out.lt_entries.push_back(a);
+            out.lt_entries.push_back(b);
+        };
+        for (uint32_t ln = 0; ln < d->n_light_nodes; ++ln) {
+            if (d->light_node_left[ln] >= 0 && d->light_node_right[ln] >= 0) continue;
+            const uint32_t L = (uint32_t)d->light_node_prim[ln];
+            out.lt_off[ln] = (int)(out.lt_entries.size() / 2);
+            entry(L);
+            int cnt = 1;
+            for (uint32_t q = 0; q < d->n_prims && cnt >= 0; ++q) {
+                if (q == L) continue;
+                bool overlap = true;
+                for (int k = 0; k < 3; ++k)
+                    if (pb[q].mn[k] - delta > pb[L].mx[k] + delta || pb[q].mx[k] + delta < pb[L].mn[k] - delta) overlap = false;
+                if (!overlap) continue;
+                if (cnt > kMaxLightNeighbours) { cnt = -1; break; }
+                entry(q);
+                cnt++;
+            }
+            if (cnt < 0) out.lt_entries.resize((size_t)out.lt_off[ln] * 2);
+            out.lt_cnt[ln] = cnt;
+        }
+        if (out.lt_entries.empty()) out.lt_entries.push_back(make_float4(0, 0, 0, 0));
+    }
     out.mats.resize(d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const b2pt_material &s = d->materials[i];

@@ -54,6 +54,7 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast) {
     v.mats = h->packed.mats.data();
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
     v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
+    v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height; v.env = h->packed.env.data();
     for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
     v.rr_rate = d->rr_rate; v.inv_rr = d->inv_rr; v.enable_shadow = d->enable_shadow; v.n_dir = d->n_dir_sample;
@@ -86,13 +87,13 @@ void hc_shadow(void *h, const float *o, const float *d, const float *dist, long 
         visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st) ? 1 : 0;
     }
 }
-// as the render path calls it: with the id of the sampled light triangle
-void hc_shadow_prim(void *h, const float *o, const float *d, const float *dist, const int *light_prim, long n, int *visible) {
+// as the render path calls it: with the light-tree leaf the sample came from (neighbourhood table first)
+void hc_shadow_lnode(void *h, const float *o, const float *d, const float *dist, const int *lnode, long n, int *visible) {
     const SceneView &S = ((HcScene *)h)->view;
 #pragma omp parallel for schedule(dynamic, 256)
     for (long i = 0; i < n; ++i) {
         TravStats st{0, 0};
-        visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st, light_prim[i]) ? 1 : 0;
+        visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st, lnode[i]) ? 1 : 0;
     }
 }
 void hc_surface(void *h, const float *o, const float *d, long n, float *coords, float *normal, float *uv) {
@@ -171,9 +172,9 @@ void hc_sample_light(void *h, const float *u4, long n, float *coords, float *nor
         pdf[i] = ls.pdf;
     }
 }
-void hc_sample_light_prim(void *h, const float *u4, long n, int *prim) {
+void hc_sample_light_node(void *h, const float *u4, long n, int *prim) {
     const SceneView &S = ((HcScene *)h)->view;
-    for (long i = 0; i < n; ++i) prim[i] = sample_light(S, u4[4 * i], u4[4 * i + 1], u4[4 * i + 2], u4[4 * i + 3]).prim;
+    for (long i = 0; i < n; ++i) prim[i] = sample_light(S, u4[4 * i], u4[4 * i + 1], u4[4 * i + 2], u4[4 * i + 3]).node;
 }
 void hc_camera_rays(const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count, unsigned long long seed,
                     float *o, float *d) {

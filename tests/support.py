@@ -311,16 +311,16 @@ class HostCheck:
         self.L.hc_shadow(self.h, fp(o), fp(d), fp(s), C.c_long(len(o)), ip(vis))
         return vis
 
-    def shadow_with_light_prim(self, o, d, dist, light_prim):
+    def shadow_with_light_node(self, o, d, dist, light_prim):
         o, d, s, lp = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3), f32(dist), i32(light_prim)
         vis = np.zeros(len(o), np.int32)
-        self.L.hc_shadow_prim(self.h, fp(o), fp(d), fp(s), ip(lp), C.c_long(len(o)), ip(vis))
+        self.L.hc_shadow_lnode(self.h, fp(o), fp(d), fp(s), ip(lp), C.c_long(len(o)), ip(vis))
         return vis
 
-    def sample_light_prim(self, u4):
+    def sample_light_node(self, u4):
         u = f32(u4).reshape(-1, 4)
         prim = np.zeros(len(u), np.int32)
-        self.L.hc_sample_light_prim(self.h, fp(u), C.c_long(len(u)), ip(prim))
+        self.L.hc_sample_light_node(self.h, fp(u), C.c_long(len(u)), ip(prim))
         return prim
 
     def surface(self, o, d):

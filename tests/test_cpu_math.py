@@ -109,7 +109,7 @@ def test_shadow_decision(world):
     assert np.array_equal(got, want), f"{name}: {(got != want).sum()} of {len(want)} visibility decisions differ"
     assert 0.01 < want.mean() < 0.99
     # the render path also passes the sampled light triangle (tested first): same decisions
-    got2 = hc.shadow_with_light_prim(p, ws, dist, hc.sample_light_prim(u4))
+    got2 = hc.shadow_with_light_node(p, ws, dist, hc.sample_light_node(u4))
     assert np.array_equal(got2, want)
 
 
