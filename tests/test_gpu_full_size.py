@@ -109,3 +109,33 @@ def test_material_sweep_cornell(ctx):
         assert ok.mean() >= 0.999, (name, (~ok).sum())
         assert np.isfinite(g).all() and g.mean() > 0.01, name
         ref.close(); sc.close()
+
+
+def test_gem_scene_deep_refraction(ctx):
+    """configs[3]: every chess piece smooth_glass_gem (A 1.3, B 0.2: strong dispersion) — deep dielectric paths, wavelengths
+    split at the first refraction.  Low-poly meshes replayed against the oracle per sample; the high-poly meshes (296 k
+    triangles, needs the model_quality fix) checked through properties."""
+    if S.have_ref():
+        sc, env = scenes.chess(128, 72, dof=True, sky=True, king="smooth_glass_gem", left="smooth_glass_gem", right="smooth_glass_gem")
+        ctx.upload(sc)
+        ref = S.Ref(sc, env)
+        px = np.random.RandomState(5).choice(128 * 72, 500, replace=False).astype(np.int32)
+        g, st = ctx.render_samples(sc.camera, px, 0, 8)
+        r = ref.render_samples(px, 0, 8)
+        ok = np.abs(g - r) <= 1e-5 + 2e-4 * np.maximum(np.abs(g), np.abs(r))
+        assert ok.mean() >= 0.999, f"{(~ok).sum()} of {ok.size} differ"
+        assert st.max_depth >= 4  # chains inside the glass (rr 0.4: P(depth >= d) = 0.4^d)
+        assert st.rays_traced_closest > len(px) * 8 and st.rays_reference > 3 * st.rays_traced_closest * 0.5
+        ref.close(); sc.close()
+    hi, env = scenes.chess(640, 360, dof=True, sky=True, quality="high", fix=b2pt.FIX_MODEL_QUALITY, king="smooth_glass_gem",
+                           left="smooth_glass_gem", right="smooth_glass_gem")
+    assert hi.desc.n_prims > 250000
+    ctx.upload(hi)
+    fb, st = ctx.render(hi.camera, 4)
+    fb2, st2 = ctx.render(hi.camera, 4, flags=b2pt.FLAG_SPLIT_WAVELENGTHS)
+    assert np.isfinite(fb).all() and np.allclose(fb, fb2, rtol=2e-5, atol=2e-6)
+    assert st.rays_reference == st2.rays_reference
+    o, d = ctx.camera_rays(hi.camera, np.arange(0, 640 * 360, 97, dtype=np.int32), 0, 1)
+    prim, t, cnt = ctx.intersect(o, d, count=True)
+    assert (prim >= 0).mean() > 0.3 and cnt.nodes_fetched / len(o) < 120
+    hi.close()

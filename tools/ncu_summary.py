@@ -34,7 +34,10 @@ def main(path):
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
         print("=" * 100)
-        print(r[hdr.index("Kernel Name")][:140])
+        name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        if "Function Name" in hdr and (not name or name.startswith("_Z")):
+            name = r[hdr.index("Function Name")]
+        print("KERNEL " + name[:140])
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
