@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-dof", action="store_true", help="configs[2]: DoF off, black environment")
     ap.add_argument("--quality", default="low", choices=["low", "high"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--queue", type=int, default=0, help="ray queue target (0 = library default)")
     ap.add_argument("--cpu-sample-spp", type=int, default=1, help="spp of the bounded CPU sample (full frame)")
     return ap.parse_args()
 
@@ -246,17 +247,17 @@ def run_ours(args):
 
     def step_device(step, flags=0):
         fb.zero_()
-        st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step, flags=flags)
+        st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step, flags=flags, max_wave_bundles=args.queue)
         reduce_frame(fb, dist, 0)
         return st
 
     def step_e2e(step):
         host_np[...] = 0
         if dist is None:
-            _, st = ctx.render(cam, spp_total, seed=S.SEED + step, sample_begin=0, sample_count=S_step, out=host_np)
+            _, st = ctx.render(cam, spp_total, seed=S.SEED + step, sample_begin=0, sample_count=S_step, out=host_np, max_wave_bundles=args.queue)
         else:
             fb.copy_(host_fb, non_blocking=True)
-            st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step)
+            st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step, max_wave_bundles=args.queue)
             reduce_frame(fb, dist, 0)
             if rank == 0:
                 host_fb.copy_(fb, non_blocking=True)

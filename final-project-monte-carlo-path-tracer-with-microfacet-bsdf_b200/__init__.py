@@ -21,7 +21,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 ASSET_DIR = os.path.join(ROOT, "assets", "models")
 HOST_LIB = os.path.join(PKG_DIR, "libb2pt_host.so")
-GPU_LIB = os.path.join(PKG_DIR, "libb2pt.so")
+GPU_LIB = os.environ.get("B2PT_GPU_LIB", os.path.join(PKG_DIR, "libb2pt.so"))  # override: experiments with kernel variants
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
