@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
 // Persistent warps with dynamic ray fetch: the walks of a warp's 32 rays are stepped together; when the
 // number of lanes still walking falls to kRefillBelow the idle lanes take new rays from the queue (one
 // warp-aggregated atomic), so a few long walks do not leave the warp mostly empty.
-constexpr int kRefillBelow = 20;
+#ifndef B2PT_REFILL_BELOW
+#define B2PT_REFILL_BELOW 12  // measured: flat between 6 and 20, worse above
+#endif
+constexpr int kRefillBelow = B2PT_REFILL_BELOW;
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
