@@ -202,6 +202,12 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ctypes_sizeof_inputs(b2pt):
+    """Bytes a render step sends to the device: the camera and the render parameters (the scene is resident)."""
+    import ctypes
+    return ctypes.sizeof(b2pt.Camera) + ctypes.sizeof(b2pt.RenderParams)
+
+
 def cam_pixels(sc):
     return sc.camera.width * sc.camera.height
 
@@ -252,11 +258,12 @@ def run_ours(args):
         return st
 
     def step_e2e(step):
-        host_np[...] = 0
         if dist is None:
-            _, st = ctx.render(cam, spp_total, seed=S.SEED + step, sample_begin=0, sample_count=S_step, out=host_np, max_wave_bundles=args.queue)
+            # a fresh frame into the caller's pinned buffer: camera + parameters go down, the frame comes back
+            _, st = ctx.render(cam, spp_total, seed=S.SEED + step, sample_begin=0, sample_count=S_step, out=host_np, max_wave_bundles=args.queue,
+                               flags=b2pt.FLAG_FRESH_FRAME)
         else:
-            fb.copy_(host_fb, non_blocking=True)
+            fb.zero_()
             st = ctx.render_device(cam, spp_total, fb.data_ptr(), sample_begin=my_begin, sample_count=my_count, seed=S.SEED + step, max_wave_bundles=args.queue)
             reduce_frame(fb, dist, 0)
             if rank == 0:
@@ -344,7 +351,7 @@ def run_ours(args):
             "projected_s_2048spp": 2048.0 * pix / spp_per_s,
             "rays_per_path": rays_all / (paths_step * world * K),
             "traced_rays_per_s_M": (rays_closest + rays_shadow) / (gpu_ms * 1e-3) / 1e6,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": pix * 12, "d2h_bytes_per_step": pix * 12,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes_sizeof_inputs(b2pt), "d2h_bytes_per_step": pix * 12,
                     "ms_per_step": e2e_ms_max / K},
             "gpu_launches": int(launches_all),
             "clocks": clocks,

@@ -31,6 +31,7 @@ c_double_p = C.POINTER(C.c_double)
 SMOOTH_CONDUCTOR, ROUGH_CONDUCTOR, SMOOTH_DIELECTRIC, ROUGH_DIELECTRIC = 0, 1, 2, 3
 FLAG_COUNT_TRAVERSAL = 1
 FLAG_SPLIT_WAVELENGTHS = 2
+FLAG_FRESH_FRAME = 4
 FIX_DIRECT_LIGHT_SAMPLE, FIX_MODEL_QUALITY, FIX_ADD_DIAMOND, FIX_OUTPUT_PATH = 1, 2, 4, 8
 NAMED_MATERIALS = ["rough_red_conductor", "rough_white_conductor", "green_mirror", "gold_conductor", "silver_mirror",
                    "smooth_glass", "smooth_glass_gem", "clear_rough_plastic", "rough_plastic"]
@@ -431,7 +432,8 @@ class Context:
     def render(self, cam: Camera, spp, seed=0x5EED0001, sample_begin=0, sample_count=0, out=None, max_wave_bundles=0, flags=0):
         """Host-buffer frame: adds sum_k rgb_k / spp into `out` ([H, W, 3] fp32) and returns (out, stats)."""
         if out is None:
-            out = np.zeros((cam.height, cam.width, 3), np.float32)
+            out = np.empty((cam.height, cam.width, 3), np.float32)
+            flags |= FLAG_FRESH_FRAME  # nothing to accumulate into
         p = self._params(spp, sample_begin, sample_count, seed, max_wave_bundles, flags)
         st = Stats()
         self._ck(self.L.b2pt_render(self.h, C.byref(cam), C.byref(p), fp(out), C.byref(st)))

@@ -42,7 +42,7 @@ constexpr int kBlock = 128;
 #define B2PT_SHADE_MIN_BLOCKS 8  // 64 registers: the shade kernels are latency-bound, occupancy beats the few spills (measured +3.7 %)
 #endif
 constexpr uint32_t kNoShadow = 0xFFFFFFFFu;
-constexpr int kClasses = 5;  // 0 terminal (miss / emitter), 1 + MaterialType otherwise
+constexpr int kClasses = 9;  // 0 terminal (miss / emitter); else 1 + 2 * MaterialType + (the path survives Russian roulette here)
 constexpr int CLASS_TERMINAL = 0;
 constexpr uint32_t INFO_DIM_MASK = 0xFFFFFu;  // bits 0-19: next draw of the path stream
 constexpr int INFO_MASK_SHIFT = 20;            // bits 20-22: wavelength paths on this ray
@@ -54,7 +54,7 @@ thread_local std::string g_create_error;
 // ---- device counters ---------------------------------------------------------------------------
 struct Counters {
     unsigned int n_cur, n_next, n_shadow, n_vis;  // n_shadow: shadow rays queued for traversal; n_vis: visibility slots handed out
-    unsigned int n_class[8];
+    unsigned int n_class[12];
     unsigned int fetch_extend, fetch_shadow;  // dynamic-fetch cursors of the traversal kernels
     unsigned int pad1[2];
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
@@ -290,7 +290,13 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                 hit_point(S, r, prim, hit_t[i], &p, &nn, &mat, &kind);
                 const Material &m = S.mats[mat];
                 if (!m.emissive) {
-                    cls = 1 + m.type;
+                    // Russian roulette is decided by a draw whose position in the stream is already known (after the
+                    // microfacet-normal and light-sample draws, Scene.cpp:121): vertices that end here and vertices that
+                    // continue are shaded by different kernels, so neither runs half-empty warps.
+                    const uint32_t dim_rr = (info & INFO_DIM_MASK) + (mat_is_rough(m) ? 2u : 0u) + 4u * ndir;
+                    Stream rr_s = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), STREAM_PATH, dim_rr);
+                    const bool survives = stream_next(rr_s) < S.rr_rate;
+                    cls = 1 + 2 * m.type + (survives ? 1 : 0);
                     want = S.enable_shadow != 0;
                 }
             }
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(kBlock) terminal_kernel(SceneView S, Queue qi,
 }
 
 // ---- shade: one vertex of Scene::castRay (Scene.cpp:109-183) on a surface of material type TYPE -------------------------
-template <int TYPE>
+template <int TYPE, bool CONT>
 __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(SceneView S, Queue qi, Queue qo, const uint32_t *__restrict__ list,
                                                        const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
                                                        const float *__restrict__ hit_t, const uint32_t *__restrict__ sh_base,
@@ -562,13 +568,14 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
 #pragma unroll
             for (int j = 0; j < 3; ++j) ldir[j] = inner ? (float)((1. - (double)kr[j]) * (double)ldir[j]) : kr[j] * ldir[j];
 
-            const float rr = stream_next(st), rd = stream_next(st);
-            const uint32_t new_dim = st.dim;
-            if (rr >= S.rr_rate) {  // Scene.cpp:129-131,156-158: the raw l_dir is returned
+            if (!CONT) {  // rr >= rrRate (decided in light_kernel): the raw l_dir is returned, Scene.cpp:129-131,156-158
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                     if (j < rs.nch) atomicAdd(acc + rs.ch[j], phi_apply(rs.phi[j], ldir[j]) / sp.div);
             } else {
+                stream_next(st);  // rr: already used by the classification
+                const float rd = stream_next(st);
+                const uint32_t new_dim = st.dim;
                 const bool back = dot(wo, mfn) < 0;
                 const float cosn = fabsf(dot(wo, nrm));
                 const f3 p_refl = back ? s.p - nrm * kEps : s.p + nrm * kEps;  // Scene.cpp:124-128
@@ -619,6 +626,7 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
                 new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT);
             }
         }
+        if (!CONT) continue;
         // append the continuation rays: warp scan over "emits >= 1 / 2 / 3 rays"
         unsigned b1 = __ballot_sync(0xffffffffu, n_emit >= 1);
         unsigned b2 = CONDUCTOR ? 0u : __ballot_sync(0xffffffffu, n_emit >= 2), b3 = CONDUCTOR ? 0u : __ballot_sync(0xffffffffu, n_emit >= 3);
@@ -976,11 +984,13 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             const uint32_t *L = ctx->wb.lists;
             const size_t cap = qa.cap;
             terminal_kernel<<<g, kBlock, 0, st>>>(S, qa, L, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
-#define SHADE(T) shade_kernel<T><<<g, kBlock, 0, st>>>(S, qa, qb, L + (size_t)(1 + T) * cap, &dc->n_class[1 + T], ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, dc, sp)
-            SHADE(MAT_SMOOTH_CONDUCTOR); SHADE(MAT_ROUGH_CONDUCTOR); SHADE(MAT_SMOOTH_DIELECTRIC); SHADE(MAT_ROUGH_DIELECTRIC);
+#define SHADE(T, C) shade_kernel<T, C><<<g, kBlock, 0, st>>>(S, qa, qb, L + (size_t)(1 + 2 * T + (C ? 1 : 0)) * cap, &dc->n_class[1 + 2 * T + (C ? 1 : 0)], \
+                                                          ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, dc, sp)
+            SHADE(MAT_SMOOTH_CONDUCTOR, false); SHADE(MAT_SMOOTH_CONDUCTOR, true); SHADE(MAT_ROUGH_CONDUCTOR, false); SHADE(MAT_ROUGH_CONDUCTOR, true);
+            SHADE(MAT_SMOOTH_DIELECTRIC, false); SHADE(MAT_SMOOTH_DIELECTRIC, true); SHADE(MAT_ROUGH_DIELECTRIC, false); SHADE(MAT_ROUGH_DIELECTRIC, true);
 #undef SHADE
             swap_counts_kernel<<<1, 1, 0, st>>>(dc);
-            launches += 6;
+            launches += 10;
         }
         cur ^= 1;
         CU(cudaMemcpyAsync(ctx->h_cnt, dc, 16, cudaMemcpyDeviceToHost, st));
@@ -1218,7 +1228,8 @@ int b2pt_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params 
     size_t bytes = (size_t)cam->width * cam->height * 3 * sizeof(float);
     int r = ensure(ctx, ctx->fb, bytes);
     if (r) return r;
-    CU(cudaMemcpyAsync(ctx->fb.p, out_rgb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (p && (p->flags & B2PT_FLAG_FRESH_FRAME)) CU(cudaMemsetAsync(ctx->fb.p, 0, bytes, ctx->stream));
+    else CU(cudaMemcpyAsync(ctx->fb.p, out_rgb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     RenderJob job{0, nullptr, 0, (float *)ctx->fb.p};
     r = run_render(ctx, cam, p, job, stats);
     if (r) return r;

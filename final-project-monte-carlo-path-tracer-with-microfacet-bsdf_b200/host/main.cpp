@@ -101,6 +101,7 @@ int main(int argc, char **argv) {
         b2pt_render_params p{};
         p.spp_total = total_spp; p.sample_begin = s0; p.sample_count = std::min(chunk, total_spp - s0);
         p.seed = seed;
+        if (s0 == 0) p.flags |= B2PT_FLAG_FRESH_FRAME;  // first chunk starts the frame, later chunks accumulate
         b2pt_stats st{};
         if (b2pt_render(ctx, cam, &p, framebuffer.data(), &st) != B2PT_OK) { std::fprintf(stderr, "\nb2pt_render: %s\n", b2pt_last_error(ctx)); return 1; }
         rays += st.rays_reference;

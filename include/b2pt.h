@@ -138,6 +138,9 @@ typedef struct b2pt_render_params {
 enum {
     B2PT_FLAG_NONE = 0,
     B2PT_FLAG_COUNT_TRAVERSAL = 1,  /* count nodes/prims fetched (stats build of the traversal kernels)            */
+    B2PT_FLAG_FRESH_FRAME = 4,      /* b2pt_render only: out_rgb is OVERWRITTEN with this call's samples (a fresh frame, like the
+                                       zero-initialised `framebuffer` of Renderer.cpp:23) instead of accumulated into: the
+                                       caller need not zero it and nothing but the camera and parameters goes to the device */
     B2PT_FLAG_SPLIT_WAVELENGTHS = 2 /* trace the R, G, B paths of a sample as three separate rays from the camera
                                        on (what the reference does, Renderer.cpp:77-79) instead of sharing rays
                                        while their geometry coincides; same result, used as a self-check          */

@@ -1,0 +1,102 @@
+"""Edge cases through the C ABI: empty batches, a scene without lights, a single-primitive scene, a sphere-only scene,
+1-pixel frames, odd frame sizes (tiles overhang the image), scene re-upload, argument errors."""
+import numpy as np
+import pytest
+
+import scenes
+import support as S
+
+b2pt = S.b2pt
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b2pt.Context(0)
+    yield c
+    c.close()
+
+
+def test_empty_batches(ctx):
+    sc, _ = scenes.two_triangle_scene()
+    ctx.upload(sc)
+    z3 = np.zeros((0, 3), np.float32)
+    prim, t = ctx.intersect(z3, z3)
+    assert prim.shape == (0,) and t.shape == (0,)
+    assert ctx.shadow(z3, z3, np.zeros(0, np.float32)).shape == (0,)
+    assert ctx.env_lookup(z3).shape == (0, 3)
+    hit, t = ctx.tri_intersect(np.zeros((0, 9), np.float32), z3, z3)
+    assert hit.shape == (0,)
+    sc.close()
+
+
+def test_scene_without_lights_and_single_primitive(ctx):
+    sc = b2pt.HostScene.empty()
+    sc.add_triangles(np.array([[-1, 0, 5, 1, 0, 5, 0, 1, 5]], np.float32), sc.find_material("rough_white_conductor"))
+    sc.set_background((0.25, 0.5, 0.75))
+    sc.set_camera(9, 7, 60.0, (0, 0.3, 0), (0, 0.3, 5))
+    sc.build_tree()
+    assert sc.desc.n_lights == 0 and sc.desc.n_prims == 1
+    ctx.upload(sc)
+    fb, st = ctx.render(sc.camera, 8)
+    assert fb.shape == (7, 9, 3) and np.isfinite(fb).all()
+    assert np.allclose(fb[0, 0], [0.25, 0.5, 0.75])  # corner pixels miss: background colour, unclamped
+    if S.have_ref():
+        ref = S.Ref(sc)
+        px = np.arange(63, dtype=np.int32)
+        g, _ = ctx.render_samples(sc.camera, px, 0, 8)
+        r = ref.render_samples(px, 0, 8)
+        assert np.allclose(g, r, rtol=2e-4, atol=1e-5)
+        ref.close()
+    sc.close()
+
+
+def test_sphere_only_scene_and_one_pixel(ctx):
+    sc = b2pt.HostScene.empty()
+    light = sc.add_material("light", b2pt.Material(b2pt.ROUGH_CONDUCTOR, (30.0, 30.0, 30.0), 1.74, 0.1, 1.0, (0, 0, 0), 0, 0))
+    sc.add_sphere((0, 0, 10), 3.0, sc.find_material("smooth_glass"))
+    sc.add_sphere((4, 1, 12), 2.0, sc.find_material("rough_plastic"))
+    sc.add_triangles(np.array([[-3, 8, 8, 3, 8, 12, 3, 8, 8], [-3, 8, 8, -3, 8, 12, 3, 8, 12]], np.float32), light)
+    sc.set_camera(1, 1, 50.0, (0, 0, 0), (0, 0, 10))
+    sc.build_tree()
+    ctx.upload(sc)
+    fb, st = ctx.render(sc.camera, 64)
+    assert fb.shape == (1, 1, 3) and np.isfinite(fb).all() and st.bundles == 64
+    if S.have_ref():
+        ref = S.Ref(sc)
+        g, _ = ctx.render_samples(sc.camera, np.zeros(1, np.int32), 0, 64)
+        r = ref.render_samples(np.zeros(1, np.int32), 0, 64)
+        assert np.allclose(g, r, rtol=2e-4, atol=1e-5)
+        ref.close()
+    sc.close()
+
+
+def test_odd_sizes_and_reupload(ctx):
+    for (w, h) in [(13, 5), (8, 4), (9, 3), (33, 17)]:
+        sc, _ = scenes.cornell(w, h)
+        ctx.upload(sc)  # re-upload replaces the previous scene
+        fb, st = ctx.render(sc.camera, 2)
+        assert fb.shape == (h, w, 3) and st.bundles == w * h * 2
+        assert (fb.reshape(-1, 3).max(axis=1) > 0).mean() > 0.9  # every pixel received its samples (tiles overhang the edges)
+        sc.close()
+
+
+def test_argument_errors(ctx):
+    sc, _ = scenes.two_triangle_scene()
+    ctx.upload(sc)
+    cam = sc.camera
+    with pytest.raises(RuntimeError):
+        ctx.render_samples(cam, np.array([cam.width * cam.height], np.int32), 0, 1)  # pixel out of range
+    with pytest.raises(RuntimeError):
+        ctx.bsdf_eval(999, np.zeros((1, 3)), np.zeros((1, 3)), np.zeros((1, 3)), [0], np.zeros((1, 2)), [1])
+    with pytest.raises(RuntimeError):
+        ctx.render(cam, 0)  # spp_total must be positive
+    # a broken scene description is rejected by validation, not by a crash
+    d = sc.desc
+    saved = d.nodes[0].a
+    d.nodes[0].a = 10 ** 9
+    with pytest.raises(RuntimeError):
+        ctx.upload(sc)
+    d.nodes[0].a = saved
+    ctx.upload(sc)
+    sc.close()

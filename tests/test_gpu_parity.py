@@ -207,6 +207,10 @@ def test_frame_matches_oracle_frame(ctx, world):
     half, _ = ctx.render(cam, spp, sample_begin=0, sample_count=2)
     half, _ = ctx.render(cam, spp, sample_begin=2, sample_count=2, out=half)
     assert np.allclose(half, fb_g, rtol=1e-5, atol=1e-6)
+    # FRESH_FRAME overwrites whatever the caller's buffer held
+    junk = np.full_like(fb_g, 123.0)
+    fresh, _ = ctx.render(cam, spp, out=junk, flags=b2pt.FLAG_FRESH_FRAME)
+    assert fresh is junk and np.allclose(fresh, fb_g, rtol=1e-5, atol=1e-6)
     # small waves give the same frame as one big wave
     small, st2 = ctx.render(cam, spp, max_wave_bundles=4096)
     assert st2.waves > st.waves
