@@ -41,13 +41,10 @@ def test_scene_without_lights_and_single_primitive(ctx):
     fb, st = ctx.render(sc.camera, 8)
     assert fb.shape == (7, 9, 3) and np.isfinite(fb).all()
     assert np.allclose(fb[0, 0], [0.25, 0.5, 0.75])  # corner pixels miss: background colour, unclamped
-    if S.have_ref():
-        ref = S.Ref(sc)
-        px = np.arange(63, dtype=np.int32)
-        g, _ = ctx.render_samples(sc.camera, px, 0, 8)
-        r = ref.render_samples(px, 0, 8)
-        assert np.allclose(g, r, rtol=2e-4, atol=1e-5)
-        ref.close()
+    # (no oracle comparison: without emitters Scene::sampleLight leaves `pdf` and the sampled point uninitialised — the
+    # reference's result is undefined; here the direct term is exactly zero)
+    hit = fb.reshape(-1, 3)[(np.abs(fb.reshape(-1, 3) - [0.25, 0.5, 0.75]) > 1e-6).any(axis=1)]
+    assert len(hit) > 0 and (hit >= 0).all() and (hit <= 5.0 + 1e-5).all()  # only the clamped env term remains
     sc.close()
 
 
@@ -77,7 +74,11 @@ def test_odd_sizes_and_reupload(ctx):
         ctx.upload(sc)  # re-upload replaces the previous scene
         fb, st = ctx.render(sc.camera, 2)
         assert fb.shape == (h, w, 3) and st.bundles == w * h * 2
-        assert (fb.reshape(-1, 3).max(axis=1) > 0).mean() > 0.9  # every pixel received its samples (tiles overhang the edges)
+        if S.have_ref():  # every pixel received exactly its samples (tiles overhang the image edges)
+            ref = S.Ref(sc)
+            want = ref.render_frame(0, 2, 2)
+            assert np.allclose(fb, want, rtol=5e-4, atol=2e-5)
+            ref.close()
         sc.close()
 
 
