@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=16, help="samples per pixel per GPU per step")
+    ap.add_argument("--spp-per-step", type=int, default=64, help="samples per pixel per GPU per step")
     ap.add_argument("--ndir", type=int, default=4, help="next-event samples per vertex (reference effective value: 4)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)

@@ -14,7 +14,7 @@
 //   --conf PATH            another conf.json                   --device D                        CUDA device
 //   --fix-ndir --fix-quality --fix-diamond --fix-output        opt-in corrections (include/b2pt_host.h)
 //   --ndir N               next-event samples per vertex       --seed S                          sample-stream key
-//   --chunk N              samples per pixel per b2pt_render call (progress granularity; default 16)
+//   --chunk N              samples per pixel per b2pt_render call (progress granularity; default 64)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -46,7 +46,7 @@ int main(int argc, char **argv) {
     bool demo = false;
 #endif
     std::string conf = "conf.json", run_dir = ".";
-    int spp = 0, width = 0, height = 0, device = 0, fix = 0, ndir = 0, chunk = 16;
+    int spp = 0, width = 0, height = 0, device = 0, fix = 0, ndir = 0, chunk = 64;
     unsigned long long seed = 0x5EED0001ull;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
