@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--quality", default="low", choices=["low", "high"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--queue", type=int, default=0, help="ray queue target (0 = library default)")
-    ap.add_argument("--cpu-sample-spp", type=int, default=1, help="spp of the bounded CPU sample (full frame)")
+    ap.add_argument("--cpu-sample-spp", type=int, default=3, help="spp of the bounded CPU sample (full frame)")
     return ap.parse_args()
 
 
@@ -171,7 +171,7 @@ def run_reference(args):
     import support as S
 
     if not S.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so is not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so is not built (needs /root/reference at build time)"})
         return
     sc, env_png = make_scene(args)
     ratio_file = os.path.join(ROOT, "profiles", "rays_per_path.json")
@@ -199,7 +199,7 @@ def run_reference(args):
                                    f"8 OpenMP threads (hard-coded), rays = paths x {rays_per_path:.3f} rays/path"},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def ctypes_sizeof_inputs(b2pt):
@@ -387,14 +387,28 @@ def run_ours(args):
                 "seconds": tt, "spp_per_s": pix * args.cpu_sample_spp / tt,
                 "sample": f"Renderer::Render of the unmodified reference (oracle/_ref), full {cam.width}x{cam.height} frame at "
                           f"spp={args.cpu_sample_spp}, 8 OpenMP threads (hard-coded in Renderer.cpp:16), rays = paths x measured rays/path"}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE line of this run, on the real stdout."""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = 1
+
+
 def main():
+    global REAL_STDOUT
+    # Everything else that writes to fd 1 (the reference's own printf/cout chatter when its scene is built and rendered)
+    # goes to stderr, so stdout carries exactly one JSON line.
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
