@@ -190,6 +190,7 @@ def gpu_lib():
         L.b2pt_update_scene_params.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
         rp, st = C.POINTER(RenderParams), C.POINTER(Stats)
         L.b2pt_render.argtypes = [C.c_void_p, C.POINTER(Camera), rp, c_float_p, st]
+        L.b2pt_group_render.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Camera), rp, c_float_p, st]
         L.b2pt_render_device.argtypes = [C.c_void_p, C.POINTER(Camera), rp, C.c_void_p, st]
         L.b2pt_render_samples.argtypes = [C.c_void_p, C.POINTER(Camera), rp, c_int_p, C.c_int32, c_float_p, st]
         L.b2pt_intersect_batch.argtypes = [C.c_void_p, c_float_p, c_float_p, C.c_int64, c_int_p, c_double_p, st]
@@ -559,3 +560,28 @@ class Context:
         g = C.c_double()
         self._ck(self.L.b2pt_measure_copy_gbs(self.h, nbytes, iters, C.byref(g)))
         return g.value
+
+
+def group_render(contexts, cam: Camera, spp, seed=0x5EED0001, sample_begin=0, sample_count=0, out=None, flags=0):
+    """One frame over several GPUs from one host thread: spp split across `contexts` (one per device, same scene uploaded),
+    one ncclReduce of the fp32 frame onto the first device (b2pt_group_render)."""
+    L = gpu_lib()
+    if out is None:
+        out = np.empty((cam.height, cam.width, 3), np.float32)
+        flags |= FLAG_FRESH_FRAME
+    p = Context._params(spp, sample_begin, sample_count, seed, 0, flags)
+    st = Stats()
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    r = L.b2pt_group_render(arr, len(contexts), C.byref(cam), C.byref(p), fp(out), C.byref(st))
+    if r != 0:
+        raise RuntimeError(f"b2pt error {r}: " + L.b2pt_last_error(contexts[0].h).decode())
+    return out, st
+
+
+def device_count():
+    """Number of CUDA devices visible to the library's process (via the runtime the library links)."""
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0

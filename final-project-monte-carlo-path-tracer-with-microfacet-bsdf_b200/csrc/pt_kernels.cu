@@ -22,11 +22,14 @@
 // the device, the host reads one counter per bounce to know when a wave has drained.
 // There is no CPU path in this library.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b2pt.h"
@@ -1238,6 +1241,118 @@ int b2pt_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params 
     if (r) return r;
     CU(cudaMemcpyAsync(out_rgb_host, ctx->fb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return B2PT_OK;
+}
+
+// ---- several GPUs, one host thread: spp split + one ncclReduce per call -------------------------------------------------
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::vector<int> devices;
+    std::vector<void *> comms;
+    std::mutex mu;
+    bool load(std::string &err) {
+        if (lib) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define SYM(field, name) field = (decltype(field))dlsym(lib, name); if (!field) { err = std::string("NCCL symbol missing: ") + name; lib = nullptr; return false; }
+        SYM(CommInitAll, "ncclCommInitAll") SYM(CommDestroy, "ncclCommDestroy") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+        SYM(Reduce, "ncclReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        return true;
+    }
+    bool ensure(const std::vector<int> &devs, std::string &err) {
+        if (!load(err)) return false;
+        if (devs == devices && !comms.empty()) return true;
+        for (void *c : comms) CommDestroy(c);
+        comms.assign(devs.size(), nullptr);
+        int r = CommInitAll(comms.data(), (int)devs.size(), devs.data());
+        if (r != 0) { err = std::string("ncclCommInitAll: ") + GetErrorString(r); comms.clear(); devices.clear(); return false; }
+        devices = devs;
+        return true;
+    }
+};
+NcclApi g_nccl;
+}  // namespace
+
+int b2pt_group_render(b2pt_ctx **ctxs, int n, const b2pt_camera *cam, const b2pt_render_params *p, float *out_rgb_host, b2pt_stats *stats) {
+    if (!ctxs || n < 1 || !ctxs[0]) return B2PT_ERR_INVALID;
+    if (n == 1) return b2pt_render(ctxs[0], cam, p, out_rgb_host, stats);
+    b2pt_ctx *ctx = ctxs[0];
+    if (!cam || !p || !out_rgb_host || cam->width <= 0 || cam->height <= 0) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    std::vector<int> devs;
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || !ctxs[i]->has_scene) return fail(ctx, B2PT_ERR_INVALID, "every context needs the scene uploaded");
+        for (int d : devs)
+            if (d == ctxs[i]->device) return fail(ctx, B2PT_ERR_INVALID, "contexts must be on distinct devices");
+        devs.push_back(ctxs[i]->device);
+    }
+    std::lock_guard<std::mutex> lock(g_nccl.mu);
+    std::string err;
+    if (!g_nccl.ensure(devs, err)) return fail(ctx, B2PT_ERR_NCCL, err);
+    const size_t count = (size_t)cam->width * cam->height * 3, bytes = count * sizeof(float);
+    // shares: contiguous blocks, the remainder spread over the first contexts
+    std::vector<int> rc(n, B2PT_OK);
+    std::vector<b2pt_stats> st(n);
+    std::vector<std::thread> th;
+    const int base = p->sample_count / n, rem = p->sample_count % n;
+    for (int i = 0; i < n; ++i) {
+        th.emplace_back([&, i]() {
+            b2pt_ctx *c = ctxs[i];
+            if (cudaSetDevice(c->device) != cudaSuccess || ensure(c, c->fb, bytes) != 0) { rc[i] = B2PT_ERR_CUDA; return; }
+            bool from_host = i == 0 && !(p->flags & B2PT_FLAG_FRESH_FRAME);
+            cudaError_t e = from_host ? cudaMemcpyAsync(c->fb.p, out_rgb_host, bytes, cudaMemcpyHostToDevice, c->stream)
+                                      : cudaMemsetAsync(c->fb.p, 0, bytes, c->stream);
+            if (e != cudaSuccess) { rc[i] = B2PT_ERR_CUDA; return; }
+            b2pt_render_params q = *p;
+            q.sample_begin = p->sample_begin + i * base + std::min(i, rem);
+            q.sample_count = base + (i < rem ? 1 : 0);
+            RenderJob job{0, nullptr, 0, (float *)c->fb.p};
+            rc[i] = q.sample_count > 0 ? run_render(c, cam, &q, job, &st[i]) : B2PT_OK;
+            if (q.sample_count == 0) std::memset(&st[i], 0, sizeof st[i]);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[i] != B2PT_OK) return fail(ctx, rc[i], "context " + std::to_string(i) + ": " + ctxs[i]->err);
+    // one reduce of the fp32 radiance buffers onto the first device
+    int r = g_nccl.GroupStart();
+    for (int i = 0; i < n && r == 0; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        r = g_nccl.Reduce(ctxs[i]->fb.p, ctxs[i]->fb.p, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, g_nccl.comms[i], ctxs[i]->stream);
+    }
+    if (r == 0) r = g_nccl.GroupEnd();
+    if (r != 0) return fail(ctx, B2PT_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        if (cudaStreamSynchronize(ctxs[i]->stream) != cudaSuccess) return fail(ctx, B2PT_ERR_CUDA, "reduce failed on device " + std::to_string(ctxs[i]->device));
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(out_rgb_host, ctx->fb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        *stats = st[0];
+        for (int i = 1; i < n; ++i) {
+            stats->gpu_ms = std::max(stats->gpu_ms, st[i].gpu_ms);
+            stats->extend_ms = std::max(stats->extend_ms, st[i].extend_ms);
+            stats->shadow_ms = std::max(stats->shadow_ms, st[i].shadow_ms);
+            stats->kernel_launches += st[i].kernel_launches; stats->extend_launches += st[i].extend_launches; stats->shadow_launches += st[i].shadow_launches;
+            stats->bundles += st[i].bundles; stats->paths += st[i].paths;
+            stats->rays_traced_closest += st[i].rays_traced_closest; stats->rays_traced_shadow += st[i].rays_traced_shadow;
+            stats->rays_reference += st[i].rays_reference; stats->vertices_shaded += st[i].vertices_shaded;
+            stats->nodes_fetched += st[i].nodes_fetched; stats->prims_tested += st[i].prims_tested;
+            stats->max_depth = std::max(stats->max_depth, st[i].max_depth); stats->waves += st[i].waves;
+        }
+    }
     return B2PT_OK;
 }
 

@@ -15,6 +15,7 @@
 //   --fix-ndir --fix-quality --fix-diamond --fix-output        opt-in corrections (include/b2pt_host.h)
 //   --ndir N               next-event samples per vertex       --seed S                          sample-stream key
 //   --chunk N              samples per pixel per b2pt_render call (progress granularity; default 64)
+//   --gpus N               split the samples over N GPUs of this box (one NCCL reduce of the frame per call)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -46,7 +47,7 @@ int main(int argc, char **argv) {
     bool demo = false;
 #endif
     std::string conf = "conf.json", run_dir = ".";
-    int spp = 0, width = 0, height = 0, device = 0, fix = 0, ndir = 0, chunk = 64;
+    int spp = 0, width = 0, height = 0, device = 0, fix = 0, ndir = 0, chunk = 64, gpus = 1;
     unsigned long long seed = 0x5EED0001ull;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -60,6 +61,7 @@ int main(int argc, char **argv) {
         else if (a == "--ndir") ndir = std::atoi(next());
         else if (a == "--seed") seed = std::strtoull(next(), nullptr, 0);
         else if (a == "--chunk") chunk = std::max(1, std::atoi(next()));
+        else if (a == "--gpus") gpus = std::max(1, std::atoi(next()));
         else if (a == "--fix-ndir") fix |= B2PT_HOST_FIX_DIRECT_LIGHT_SAMPLE;
         else if (a == "--fix-quality") fix |= B2PT_HOST_FIX_MODEL_QUALITY;
         else if (a == "--fix-diamond") fix |= B2PT_HOST_FIX_ADD_DIAMOND;
@@ -84,9 +86,12 @@ int main(int argc, char **argv) {
     std::printf(" - Generating BVH...\n\n");  // Scene::buildBVH, src/Scene.cpp:15
     if (b2pt_host_scene_build(scene) != 0) { std::fprintf(stderr, "BVH build failed: %s\n", b2pt_host_last_error()); return 1; }
 
-    b2pt_ctx *ctx = nullptr;
-    if (b2pt_create(&ctx, device) != B2PT_OK) { std::fprintf(stderr, "b2pt_create: %s\n", b2pt_last_error(nullptr)); return 1; }
-    if (b2pt_upload_scene(ctx, b2pt_host_scene_desc(scene)) != B2PT_OK) { std::fprintf(stderr, "b2pt_upload_scene: %s\n", b2pt_last_error(ctx)); return 1; }
+    std::vector<b2pt_ctx *> ctxs(gpus, nullptr);
+    for (int g = 0; g < gpus; ++g) {
+        if (b2pt_create(&ctxs[g], device + g) != B2PT_OK) { std::fprintf(stderr, "b2pt_create: %s\n", b2pt_last_error(nullptr)); return 1; }
+        if (b2pt_upload_scene(ctxs[g], b2pt_host_scene_desc(scene)) != B2PT_OK) { std::fprintf(stderr, "b2pt_upload_scene: %s\n", b2pt_last_error(ctxs[g])); return 1; }
+    }
+    b2pt_ctx *ctx = ctxs[0];
 
     const b2pt_camera *cam = b2pt_host_scene_camera(scene);
     const int total_spp = b2pt_host_scene_spp(scene);
@@ -103,7 +108,7 @@ int main(int argc, char **argv) {
         p.seed = seed;
         if (s0 == 0) p.flags |= B2PT_FLAG_FRESH_FRAME;  // first chunk starts the frame, later chunks accumulate
         b2pt_stats st{};
-        if (b2pt_render(ctx, cam, &p, framebuffer.data(), &st) != B2PT_OK) { std::fprintf(stderr, "\nb2pt_render: %s\n", b2pt_last_error(ctx)); return 1; }
+        if (b2pt_group_render(ctxs.data(), gpus, cam, &p, framebuffer.data(), &st) != B2PT_OK) { std::fprintf(stderr, "\nb2pt_render: %s\n", b2pt_last_error(ctx)); return 1; }
         rays += st.rays_reference;
         gpu_ms += st.gpu_ms;
         update_progress((float)(s0 + p.sample_count) / (float)total_spp);
@@ -122,7 +127,7 @@ int main(int argc, char **argv) {
     std::cout << "Rendering finished in " << ms / 3600000 << ":" << (ms / 60000) % 60 << ":" << (ms / 1000) % 60 << "." << ms % 1000 << std::endl;
     std::fprintf(stderr, "[b2pt] %.1f Mrays/s on the GPU (%llu rays, %.1f ms of device time)\n", gpu_ms > 0 ? rays / gpu_ms / 1e3 : 0.0, rays, gpu_ms);
 
-    b2pt_destroy(ctx);
+    for (b2pt_ctx *c : ctxs) b2pt_destroy(c);
     b2pt_host_scene_free(scene);
     return 0;
 }

@@ -196,6 +196,13 @@ int b2pt_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params 
  * complete on return.  This is the buffer a multi-process job reduces with NCCL. */
 int b2pt_render_device(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *p, float *out_rgb_device,
                        b2pt_stats *stats);
+/* The same frame over SEVERAL GPUs of one box from one host thread: the samples
+ * [sample_begin, sample_begin + sample_count) are split into contiguous shares, context i renders its share on its own
+ * device into its own fp32 buffer, the buffers are summed onto ctxs[0]'s device with ONE ncclReduce per call (NCCL is
+ * loaded with dlopen on first use: libnccl.so.2), and the result goes to out_rgb_host like b2pt_render.  Every context
+ * must hold the same scene.  Sample streams are keyed by the global sample index, so the frame does not depend on n. */
+int b2pt_group_render(b2pt_ctx **ctxs, int n, const b2pt_camera *cam, const b2pt_render_params *p, float *out_rgb_host,
+                      b2pt_stats *stats);
 /* Per-sample radiance of listed pixels: out[(q*sample_count + k)*3 + c] = the three castRay
  * values of Renderer.cpp:77-79 for pixel pixels[q], sample sample_begin+k. */
 int b2pt_render_samples(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *p, const int32_t *pixels,
