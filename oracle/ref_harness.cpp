@@ -100,6 +100,8 @@ extern "C" void sincosf(float x, float *s, float *c) noexcept {
 #include "Triangle.hpp"
 #undef private
 
+#include "b2pt_bind.hpp"  // the reference-side binding of INTEGRATION.md, checked by tests/test_integration_binding.py
+
 struct RefScene {
     Scene scene{Camera()};
     Renderer renderer;
@@ -107,6 +109,9 @@ struct RefScene {
     std::vector<Object *> objs;       // in Scene::Add order
     std::vector<MeshTriangle *> mesh; // nullptr for spheres
     bool built = false;
+    float rr = 0.7f;  // what ref_set_* passed on (Scene has no getters)
+    bool rr_set = false, shadow = true;
+    int ndir = 4;
 };
 
 static const WaveLenType WL[3] = {RED, GREEN, BLUE};
@@ -152,9 +157,9 @@ int ref_add_sphere(void *h, const float *c, float r, int mat) {
     S->objs.push_back(s); S->mesh.push_back(nullptr);
     return (int)S->objs.size() - 1;
 }
-void ref_set_rr(void *h, float rr) { ((RefScene *)h)->scene.setRrRate(rr); }
-void ref_set_shadow(void *h, int on) { ((RefScene *)h)->scene.enableShadow(on != 0); }
-void ref_set_n_dir(void *h, int n) { ((RefScene *)h)->scene.setDirectLightSample(n); }
+void ref_set_rr(void *h, float rr) { ((RefScene *)h)->scene.setRrRate(rr); ((RefScene *)h)->rr = rr; ((RefScene *)h)->rr_set = true; }
+void ref_set_shadow(void *h, int on) { ((RefScene *)h)->scene.enableShadow(on != 0); ((RefScene *)h)->shadow = on != 0; }
+void ref_set_n_dir(void *h, int n) { ((RefScene *)h)->scene.setDirectLightSample(n); ((RefScene *)h)->ndir = n; }
 void ref_set_background(void *h, const float *rgb) { ((RefScene *)h)->scene.backgroundColor = V3(rgb); }
 int ref_load_env(void *h, const char *png) {
     RefScene *S = (RefScene *)h;
@@ -199,6 +204,24 @@ void ref_object_bounds(void *h, int obj, float *b6) {
 void ref_camera_orientation(void *h, float *m9) {
     Matrix3f O = ((RefScene *)h)->scene.camera.getOrientation();
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m9[3 * r + c] = O(r, c);
+}
+
+// ---- the INTEGRATION.md binding applied to this scene: the flattened arrays it would hand to b2pt_upload_scene -----------
+void *ref_flatten(void *h) {
+    RefScene *S = (RefScene *)h;
+    B2ptFlat *f = new B2ptFlat();
+    f->build(S->scene, S->rr_set ? S->rr : -1.f, S->shadow, S->ndir);
+    return f;
+}
+void ref_flat_free(void *f) { delete (B2ptFlat *)f; }
+const b2pt_scene_desc *ref_flat_desc(void *f) { return &((B2ptFlat *)f)->desc; }
+const b2pt_camera *ref_flat_camera(void *f) { return &((B2ptFlat *)f)->cam; }
+// material index the binding assigned to the reference Material object number `mat` (creation order), -1 if unused
+int ref_flat_material_index(void *h, void *f, int mat) {
+    RefScene *S = (RefScene *)h;
+    auto &m = ((B2ptFlat *)f)->mat_id;
+    auto it = m.find(S->mats[mat]);
+    return it == m.end() ? -1 : (int)it->second;
 }
 
 // ---- (a6) Scene::intersect on a ray batch ------------------------------------------
