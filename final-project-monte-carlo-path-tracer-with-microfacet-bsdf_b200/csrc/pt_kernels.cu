@@ -116,29 +116,6 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
-// ---- clamped-affine path state ------------------------------------------------
-struct Phi {
-    float M, K, L, U;
-};
-__device__ __forceinline__ bool phi_unbounded(const Phi &p) { return !(p.L > -INFINITY) && !(p.U < INFINITY); }
-__device__ __forceinline__ float phi_clamp(const Phi &p, float y) { return phi_unbounded(p) ? y : clamp_ref(p.L, p.U, y); }
-__device__ __forceinline__ float phi_apply(const Phi &p, float x) { return phi_clamp(p, p.M * x + p.K); }
-// phi o g with g(x) = A + clamp(0, 5, f * x): one non-terminal level of castRay (Scene.cpp:139-143,180-183).
-__device__ __forceinline__ Phi phi_compose(const Phi &p, float A, float f) {
-    float c = p.M * A + p.K, c5 = p.M * (A + 5.f) + p.K;
-    float b0 = phi_clamp(p, c), b1 = phi_clamp(p, c5);
-    Phi r;
-    if (f != f || f == INFINITY) {  // clamp(0, 5, NaN) = 5: the level is the constant A + 5
-        r.M = 0.f; r.K = b1; r.L = b1; r.U = b1;
-    } else if (f == -INFINITY) {
-        r.M = 0.f; r.K = b0; r.L = b0; r.U = b0;
-    } else {
-        r.M = p.M * f; r.K = c;
-        r.L = fminf(b0, b1); r.U = fmaxf(b0, b1);
-    }
-    return r;
-}
-
 // ---- generate: Renderer.cpp:39-76 -----------------------------------------------------------------------
 // Appends to queue `q`, whose length lives in *count (path regeneration: new camera rays top up the queue
 // every bounce, so the kernels keep working on full queues until the samples run out).

@@ -77,6 +77,29 @@ PT_HD float clamp_ref(float lo, float hi, float v) {
     return (lo < m) ? m : lo;
 }
 
+// ---- clamped-affine path state ------------------------------------------------
+struct Phi {
+    float M, K, L, U;
+};
+PT_HD bool phi_unbounded(const Phi &p) { return !(p.L > -INFINITY) && !(p.U < INFINITY); }
+PT_HD float phi_clamp(const Phi &p, float y) { return phi_unbounded(p) ? y : clamp_ref(p.L, p.U, y); }
+PT_HD float phi_apply(const Phi &p, float x) { return phi_clamp(p, p.M * x + p.K); }
+// phi o g with g(x) = A + clamp(0, 5, f * x): one non-terminal level of castRay (Scene.cpp:139-143,180-183).
+PT_HD Phi phi_compose(const Phi &p, float A, float f) {
+    float c = p.M * A + p.K, c5 = p.M * (A + 5.f) + p.K;
+    float b0 = phi_clamp(p, c), b1 = phi_clamp(p, c5);
+    Phi r;
+    if (f != f || f == INFINITY) {  // clamp(0, 5, NaN) = 5: the level is the constant A + 5
+        r.M = 0.f; r.K = b1; r.L = b1; r.U = b1;
+    } else if (f == -INFINITY) {
+        r.M = 0.f; r.K = b0; r.L = b0; r.U = b0;
+    } else {
+        r.M = p.M * f; r.K = c;
+        r.L = fminf(b0, b1); r.U = fmaxf(b0, b1);
+    }
+    return r;
+}
+
 // ---- sample streams (replace std::mt19937 + random_device, src/global.hpp:42-53) ---------------
 // Philox4x32-10; stream (pixel, sample, tag); draw `dim` = word dim&3 of block dim>>2.
 PT_HD_NI uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {

@@ -176,6 +176,15 @@ void hc_sample_light_node(void *h, const float *u4, long n, int *prim) {
     const SceneView &S = ((HcScene *)h)->view;
     for (long i = 0; i < n; ++i) prim[i] = sample_light(S, u4[4 * i], u4[4 * i + 1], u4[4 * i + 2], u4[4 * i + 3]).node;
 }
+// The clamped-affine accumulator against the recursion it replaces.  levels: per path `depth` rows of (A, f) from the
+// outermost level inwards, then the terminal value.  out_phi = the composed map applied to the terminal.
+void hc_phi_chain(const float *levels, const float *terminal, long n, int depth, float *out_phi) {
+    for (long i = 0; i < n; ++i) {
+        Phi p; p.M = 1.f; p.K = 0.f; p.L = -INFINITY; p.U = INFINITY;
+        for (int d = 0; d < depth; ++d) p = phi_compose(p, levels[(i * depth + d) * 2], levels[(i * depth + d) * 2 + 1]);
+        out_phi[i] = phi_apply(p, terminal[i]);
+    }
+}
 void hc_camera_rays(const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count, unsigned long long seed,
                     float *o, float *d) {
     Camera c = make_camera(cam);
