@@ -81,7 +81,8 @@ struct WaveBufs {
     float *hit_t;
     uint32_t *sh_base;
     uint32_t *lists;  // [kClasses][cap] ray indices by class
-    float4 *cand_o, *cand_d;  // every light sample: origin.xyz | dist, direction.xyz | light-tree leaf; indexed by visibility slot
+    float4 *vtx_pn;  // per shaded vertex: NEE origin p + n * EPSILON | position of its first light-sample draw in the stream
+    uint2 *vtx_ps;   // per shaded vertex: pixel, sample (the stream's key)
     float4 *sh_o;  // origin.xyz, w = dist
     float4 *sh_d;  // direction.xyz, w = visibility slot | phase bit
     unsigned char *vis;
@@ -249,8 +250,8 @@ __device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int 
 // Every queued ray is filed under one of five classes — terminal (miss or emitter) or the MaterialType of
 // the surface it hit — so that the shading kernels run with warps whose lanes take the same code path.
 __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
-                                                       const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ cand_o,
-                                                       float4 *__restrict__ cand_d, uint32_t *__restrict__ lists, Counters *cnt, uint32_t k0, uint32_t k1) {
+                                                       const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ vtx_pn,
+                                                       uint2 *__restrict__ vtx_ps, uint32_t *__restrict__ lists, Counters *cnt, uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
@@ -284,15 +285,16 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                 }
             }
         }
-        // file the ray under its class (warp-aggregated append per class)
-#pragma unroll
-        for (int c = 0; c < kClasses; ++c) {
-            unsigned b = __ballot_sync(0xffffffffu, cls == c);
-            if (!b) continue;
-            unsigned base = 0;
-            if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(&cnt->n_class[c], (unsigned)__popc(b));
-            base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-            if (cls == c) lists[(size_t)c * q.cap + base + (unsigned)__popc(b & lanemask_lt())] = i;
+        // file the ray under its class: lanes of the same class elect a leader that reserves their slots with one atomic
+        {
+            const unsigned grp = __match_any_sync(0xffffffffu, cls);
+            if (cls >= 0) {
+                const int leader = __ffs(grp) - 1;
+                unsigned base = 0;
+                if ((int)lane == leader) base = atomicAdd(&cnt->n_class[cls], (unsigned)__popc(grp));
+                base = __shfl_sync(grp, base, leader);
+                lists[(size_t)cls * q.cap + base + (unsigned)__popc(grp & lanemask_lt())] = i;
+            }
         }
         // visibility slots: ndir per surviving vertex
         unsigned ballot = __ballot_sync(0xffffffffu, want);
@@ -301,16 +303,12 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned vb = base + (unsigned)__popc(ballot & lanemask_lt()) * ndir;
         if (i < n) sh_base[i] = want ? vb : kNoShadow;
-        if (want) {
+        if (want) {  // one record per surviving vertex; its ndir light samples are drawn by nee_kernel, one lane each
             f3 pn = p + nn * kEps;  // inter.coords += n * EPSILON, Scene.cpp:114
             uint32_t dim = (info & INFO_DIM_MASK) + (mat_is_rough(S.mats[mat]) ? 2u : 0u);
-            Stream rs = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), STREAM_PATH, dim);
-            for (unsigned k = 0; k < ndir; ++k) {
-                float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
-                NeeGeom g = nee_geometry(S, pn, u0, u1, u2, u3);
-                cand_o[vb + k] = make_float4(pn.x, pn.y, pn.z, g.dist);
-                cand_d[vb + k] = make_float4(g.ws.x, g.ws.y, g.ws.z, __int_as_float(g.lnode));
-            }
+            const unsigned v = vb / ndir;
+            vtx_pn[v] = make_float4(pn.x, pn.y, pn.z, __uint_as_float(dim));
+            vtx_ps[v] = make_uint2(__float_as_uint(o4.w), __float_as_uint(d4.w));
             refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
         }
     }
@@ -318,23 +316,34 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
     if (lane == 0 && refs) atomicAdd(&cnt->rays_reference, refs);
 }
 
-// ---- window: the "some hit lies within EPSILON of dist" half of Scene.cpp:74-75, one lane per light sample -------------------
-// Tested against the light neighbourhood table (no traversal).  A sample whose window holds no hit is rejected here and
-// never becomes a shadow ray; the others are compacted into the shadow queue for the occluder search.
-__global__ void __launch_bounds__(kBlock) window_kernel(SceneView S, const float4 *__restrict__ cand_o, const float4 *__restrict__ cand_d,
-                                                        const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis,
-                                                        float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt) {
+// ---- nee: one lane per light sample of Scene::directLighting (Scene.cpp:63-75) ------------------------------------------------
+// Draws the sample (Scene::sampleLight on the vertex's stream), builds the shadow ray, and answers the "some hit lies within
+// EPSILON of dist" half of the visibility test from the light neighbourhood table (no traversal).  A sample whose window
+// holds no hit is rejected here and never becomes a shadow ray; the others are compacted into the shadow queue for the
+// occluder search.
+__global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *__restrict__ vtx_pn, const uint2 *__restrict__ vtx_ps,
+                                                     const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis,
+                                                     float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt, uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
+    const unsigned ndir = (unsigned)S.n_dir;
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
         const unsigned i = it + threadIdx.x;
         bool queue = false;
         int w = 0;
-        float4 o, d;
+        f3 pn = mk3(0, 0, 0);
+        NeeGeom g;
+        g.ws = mk3(0, 0, 1); g.dist = 0.f;
         if (i < n) {
-            o = cand_o[i]; d = cand_d[i];
-            w = window_witness(S, make_ray(xyz(o), xyz(d)), o.w, __float_as_int(d.w));
+            const unsigned v = i / ndir, k = i - v * ndir;
+            const float4 a = vtx_pn[v];
+            const uint2 ps = vtx_ps[v];
+            pn = xyz(a);
+            Stream rs = stream_open(k0, k1, ps.x, ps.y, STREAM_PATH, __float_as_uint(a.w) + 4u * k);
+            float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
+            g = nee_geometry(S, pn, u0, u1, u2, u3);
+            w = window_witness(S, make_ray(pn, g.ws), g.dist, g.lnode);
             if (w == 0) vis[i] = 0;
             else queue = true;
         }
@@ -346,9 +355,9 @@ __global__ void __launch_bounds__(kBlock) window_kernel(SceneView S, const float
         qbase = __shfl_sync(0xffffffffu, qbase, leader);
         if (queue) {
             unsigned q = qbase + (unsigned)__popc(qb & lanemask_lt());
-            sh_o[q] = o;
+            sh_o[q] = make_float4(pn.x, pn.y, pn.z, g.dist);
             // w == 1: a witness exists, only occluders are searched (phase 2); w < 0: no table entry, search the window first
-            sh_d[q] = make_float4(d.x, d.y, d.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
+            sh_d[q] = make_float4(g.ws.x, g.ws.y, g.ws.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
         }
     }
 }
@@ -851,7 +860,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t per_queue = al(rays * 16) * 2 + al(rays * 4) * 2 + al(rays * 16 * 6);
     size_t shadows = rays * (size_t)ndir;
-    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 4 + al(shadows);
+    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows) + al(rays * 16) + al(rays * 8);
     release(ctx->wave_mem);
     ctx->wave_rays = 0;
     int r = ensure(ctx, ctx->wave_mem, total);
@@ -869,8 +878,8 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     ctx->wb.hit_t = (float *)take(rays * 4);
     ctx->wb.sh_base = (uint32_t *)take(rays * 4);
     ctx->wb.lists = (uint32_t *)take(rays * 4 * kClasses);
-    ctx->wb.cand_o = (float4 *)take(shadows * 16);
-    ctx->wb.cand_d = (float4 *)take(shadows * 16);
+    ctx->wb.vtx_pn = (float4 *)take(rays * 16);
+    ctx->wb.vtx_ps = (uint2 *)take(rays * 8);
     ctx->wb.sh_o = (float4 *)take(shadows * 16);
     ctx->wb.sh_d = (float4 *)take(shadows * 16);
     ctx->wb.vis = (unsigned char *)take(shadows);
@@ -949,12 +958,12 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
         CU(cudaEventRecord(ctx->ev[3], st));
         launches++; ext_launches++;
-        light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.cand_o, ctx->wb.cand_d,
+        light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vtx_pn, ctx->wb.vtx_ps,
                                                            ctx->wb.lists, dc, gp.k0, gp.k1);
         launches++;
         if (S.enable_shadow) {
-            window_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.cand_o, ctx->wb.cand_d, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o,
-                                                                                   ctx->wb.sh_d, dc);
+            nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, ctx->wb.vtx_ps, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o,
+                                                                                ctx->wb.sh_d, dc, gp.k0, gp.k1);
             launches++;
             CU(cudaEventRecord(ctx->ev[4], st));
             if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
