@@ -120,11 +120,44 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
+// ---- block-aggregated queue allocation -------------------------------------------------------------------------------------
+// Appending to a queue means bumping ONE device counter.  A warp-aggregated atomic per warp still sends half a million
+// same-address atomics per launch to a single L2 location, and the launch then runs at the rate that location serialises
+// them (ncu: light_kernel 890 us with them, 130 us without).  So counts are first combined across the block in shared
+// memory and one thread issues one atomic per block per counter.  Every thread of the block must call (uniform control flow).
+constexpr int kWarps = kBlock / 32;
+__device__ __forceinline__ unsigned block_alloc(unsigned my_count, unsigned *counter, unsigned scale = 1) {
+    __shared__ unsigned s_warp[kWarps];
+    __shared__ unsigned s_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned incl = my_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) total += s_warp[w];
+        s_base = total ? atomicAdd(counter, total * scale) : 0u;
+    }
+    __syncthreads();
+    unsigned off = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+        if ((unsigned)w < warp) off += s_warp[w];
+    const unsigned r = s_base + (off + incl - my_count) * scale;
+    __syncthreads();
+    return r;
+}
+
 // ---- generate: Renderer.cpp:39-76 -----------------------------------------------------------------------
 // Appends to queue `q`, whose length lives in *count (path regeneration: new camera rays top up the queue
 // every bounce, so the kernels keep working on full queues until the samples run out).
 __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams gp, Queue q, unsigned *count) {
-    const unsigned lane = threadIdx.x & 31u;
     const unsigned long long rounded = ((unsigned long long)gp.count + kBlock - 1) / kBlock * kBlock;
     for (unsigned long long it = (unsigned long long)blockIdx.x * kBlock; it < rounded; it += (unsigned long long)gridDim.x * kBlock) {
         unsigned long long li = it + threadIdx.x;
@@ -155,12 +188,8 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
             camera_ray(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), rs, &pos, &dir);
         }
         const int per = gp.split ? 3 : 1;
-        unsigned ballot = __ballot_sync(0xffffffffu, valid);
-        unsigned base = 0;
-        if (lane == 0 && ballot) base = atomicAdd(count, (unsigned)(__popc(ballot) * per));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned p = block_alloc(valid ? 1u : 0u, count, (unsigned)per);
         if (valid) {
-            unsigned p = base + (unsigned)__popc(ballot & lanemask_lt()) * per;
             for (int k = 0; k < per; ++k) {
                 uint32_t mask = gp.split ? (1u << k) : 7u;
                 q.o[p + k] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
@@ -181,6 +210,47 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
 #endif
 constexpr int kRefillBelow = B2PT_REFILL_BELOW;
 
+// Rays are handed to the persistent warps in chunks: a warp reserves a run of consecutive rays with ONE atomic on the
+// queue cursor and refills its idle lanes from that run until it is used up (a per-refill atomic on a single address is a
+// serialisation point, see block_alloc).  The chunk shrinks with the queue so that short queues still spread over the GPU.
+struct Fetch {
+    unsigned lo, hi;  // the warp's reserved run [lo, hi)
+    unsigned chunk;
+    bool dry;         // the cursor has passed the end of the queue
+};
+__device__ __forceinline__ Fetch fetch_begin(unsigned n) {
+    Fetch F;
+    F.lo = F.hi = 0;
+    unsigned per_warp = n / (gridDim.x * kWarps * 4u);
+    F.chunk = min(256u, max(32u, per_warp & ~31u));
+    F.dry = false;
+    return F;
+}
+// Every lane calls; `idle` lanes get the index of a new ray or 0xFFFFFFFF when the queue is exhausted.
+__device__ __forceinline__ unsigned fetch_rays(Fetch &F, bool idle, unsigned n, unsigned *next, unsigned lane) {
+    const unsigned need = __ballot_sync(0xffffffffu, idle);
+    if (!need) return 0xFFFFFFFFu;
+    const unsigned cnt = (unsigned)__popc(need), rank = (unsigned)__popc(need & lanemask_lt());
+    const unsigned rem = F.hi - F.lo;
+    unsigned nlo = 0, nhi = 0;
+    if (rem < cnt && !F.dry) {
+        const int leader = __ffs(need) - 1;
+        unsigned base = 0;
+        if ((int)lane == leader) base = atomicAdd(next, F.chunk);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        nlo = min(base, n); nhi = min(base + F.chunk, n);
+        if (nhi - nlo < F.chunk) F.dry = true;
+    }
+    unsigned idx = 0xFFFFFFFFu;
+    if (idle) {
+        if (rank < rem) idx = F.lo + rank;
+        else if (rank - rem < nhi - nlo) idx = nlo + (rank - rem);
+    }
+    if (rem >= cnt) F.lo += cnt;
+    else { F.lo = nlo + min(cnt - rem, nhi - nlo); F.hi = nhi; }
+    return idx;
+}
+
 #ifndef B2PT_TRAV_MIN_BLOCKS
 #define B2PT_TRAV_MIN_BLOCKS 10  // 48 registers: 10 blocks per SM (measured +2.6 % over 56 registers / 9 blocks; 12 and 16 spill too much)
 #endif
@@ -199,26 +269,19 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) extend_kernel(Sc
     Trav T;
     r.o = r.d = r.inv = mk3(0, 0, 0);
     trav_begin(S, r, T);
+    Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
-            unsigned need = __ballot_sync(0xffffffffu, !has);
-            if (need) {
-                const int leader = __ffs(need) - 1;
-                unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(next, (unsigned)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (!has) {
-                    idx = base + (unsigned)__popc(need & lanemask_lt());
-                    if (idx < n) {
-                        float4 o = qo[idx], d = qd[idx];
-                        r = make_ray(xyz(o), xyz(d));
-                        trav_begin(S, r, T);
-                        has = true;
-                        refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                    }
-                }
-                exhausted = base + (unsigned)__popc(need) >= n;
+            const unsigned got = fetch_rays(F, !has, n, next, lane);
+            if (!has && got != 0xFFFFFFFFu) {
+                idx = got;
+                float4 o = qo[idx], d = qd[idx];
+                r = make_ray(xyz(o), xyz(d));
+                trav_begin(S, r, T);
+                has = true;
+                refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
             }
+            exhausted = F.dry && F.lo >= F.hi;
         }
         unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) break;
@@ -265,6 +328,7 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
         unsigned i = it + threadIdx.x;
         bool want = false;
         int cls = -1;
+        unsigned vb = 0;
         Ray r;
         f3 p, nn;
         uint32_t info = 0, mat = 0, kind = 0;
@@ -289,23 +353,39 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                 }
             }
         }
-        // file the ray under its class: lanes of the same class elect a leader that reserves their slots with one atomic
+        // file the ray under its class.  Per class: rank inside the warp (match_any), warps combined in shared memory, one
+        // atomic per class per block; the visibility slots of the surviving vertices are reserved the same way.
         {
+            __shared__ unsigned s_cnt[kWarps][kClasses + 1];
+            __shared__ unsigned s_off[kClasses + 1];
+            const unsigned warp = threadIdx.x >> 5;
+            if (lane <= (unsigned)kClasses) s_cnt[warp][lane] = 0;
+            __syncwarp();
             const unsigned grp = __match_any_sync(0xffffffffu, cls);
-            if (cls >= 0) {
-                const int leader = __ffs(grp) - 1;
-                unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(&cnt->n_class[cls], (unsigned)__popc(grp));
-                base = __shfl_sync(grp, base, leader);
-                lists[(size_t)cls * q.cap + base + (unsigned)__popc(grp & lanemask_lt())] = i;
+            const unsigned rank = (unsigned)__popc(grp & lanemask_lt());
+            if (cls >= 0 && rank == 0) s_cnt[warp][cls] = (unsigned)__popc(grp);
+            const unsigned wb = __ballot_sync(0xffffffffu, want);
+            if (lane == 0) s_cnt[warp][kClasses] = (unsigned)__popc(wb);
+            __syncthreads();
+            if (threadIdx.x <= (unsigned)kClasses) {
+                const int c = (int)threadIdx.x;
+                unsigned total = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) total += s_cnt[w][c];
+                unsigned *ctr = c < kClasses ? &cnt->n_class[c] : &cnt->n_vis;
+                s_off[c] = total ? atomicAdd(ctr, c < kClasses ? total : total * ndir) : 0u;
             }
+            __syncthreads();
+            if (cls >= 0) {
+                unsigned off = s_off[cls] + rank;
+                for (unsigned w = 0; w < warp; ++w) off += s_cnt[w][cls];
+                lists[(size_t)cls * q.cap + off] = i;
+            }
+            unsigned voff = (unsigned)__popc(wb & lanemask_lt());
+            for (unsigned w = 0; w < warp; ++w) voff += s_cnt[w][kClasses];
+            vb = s_off[kClasses] + voff * ndir;
+            __syncthreads();
         }
-        // visibility slots: ndir per surviving vertex
-        unsigned ballot = __ballot_sync(0xffffffffu, want);
-        unsigned base = 0;
-        if (lane == 0 && ballot) base = atomicAdd(&cnt->n_vis, (unsigned)__popc(ballot) * ndir);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned vb = base + (unsigned)__popc(ballot & lanemask_lt()) * ndir;
         if (i < n) sh_base[i] = want ? vb : kNoShadow;
         if (want) {  // one record per surviving vertex; its ndir light samples are drawn by nee_kernel, one lane each
             f3 pn = p + nn * kEps;  // inter.coords += n * EPSILON, Scene.cpp:114
@@ -330,7 +410,6 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *
                                                      const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis,
                                                      float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt, uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
-    const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
     const unsigned ndir = (unsigned)S.n_dir;
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
@@ -352,14 +431,8 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *
             if (w == 0) vis[i] = 0;
             else queue = true;
         }
-        unsigned qb = __ballot_sync(0xffffffffu, queue);
-        if (!qb) continue;
-        unsigned qbase = 0;
-        const int leader = __ffs(qb) - 1;
-        if ((int)lane == leader) qbase = atomicAdd(&cnt->n_shadow, (unsigned)__popc(qb));
-        qbase = __shfl_sync(0xffffffffu, qbase, leader);
+        const unsigned q = block_alloc(queue ? 1u : 0u, &cnt->n_shadow);
         if (queue) {
-            unsigned q = qbase + (unsigned)__popc(qb & lanemask_lt());
             sh_o[q] = make_float4(pn.x, pn.y, pn.z, g.dist);
             // w == 1: a witness exists, only occluders are searched (phase 2); w < 0: no table entry, search the window first
             sh_d[q] = make_float4(g.ws.x, g.ws.y, g.ws.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
@@ -382,28 +455,21 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
     ShadowTrav T;
     r.o = r.d = r.inv = mk3(0, 0, 0);
     shadow_begin(S, r, T, 0.f);
+    Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
-            unsigned need = __ballot_sync(0xffffffffu, !has);
-            if (need) {
-                const int leader = __ffs(need) - 1;
-                unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(next, (unsigned)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (!has) {
-                    idx = base + (unsigned)__popc(need & lanemask_lt());
-                    if (idx < n) {
-                        float4 o = sh_o[idx], d = sh_d[idx];
-                        r = make_ray(xyz(o), xyz(d));
-                        dist = o.w;
-                        const uint32_t tag = __float_as_uint(d.w);
-                        shadow_begin(S, r, T, dist, (tag & 0x80000000u) ? 1 : 2);
-                        slot = tag & 0x7FFFFFFFu;
-                        has = true;
-                    }
-                }
-                exhausted = base + (unsigned)__popc(need) >= n;
+            const unsigned got = fetch_rays(F, !has, n, next, lane);
+            if (!has && got != 0xFFFFFFFFu) {
+                idx = got;
+                float4 o = sh_o[idx], d = sh_d[idx];
+                r = make_ray(xyz(o), xyz(d));
+                dist = o.w;
+                const uint32_t tag = __float_as_uint(d.w);
+                shadow_begin(S, r, T, dist, (tag & 0x80000000u) ? 1 : 2);
+                slot = tag & 0x7FFFFFFFu;
+                has = true;
             }
+            exhausted = F.dry && F.lo >= F.hi;
         }
         unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) break;
@@ -425,7 +491,6 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
 __global__ void __launch_bounds__(kBlock) lit_kernel(const unsigned char *__restrict__ vis, const unsigned *__restrict__ n_ptr, int all_lit,
                                                      uint32_t *__restrict__ lit_list, Counters *cnt) {
     const unsigned n = *n_ptr;
-    const unsigned lane = threadIdx.x & 31u;
     const unsigned groups = (n + 3) / 4;  // four flags (one 32-bit word) per lane; the buffer is padded to a multiple of 256 bytes
     const unsigned rounded = (groups + kBlock - 1) / kBlock * kBlock;
     const uint32_t *vis4 = reinterpret_cast<const uint32_t *>(vis);
@@ -438,19 +503,7 @@ __global__ void __launch_bounds__(kBlock) lit_kernel(const unsigned char *__rest
             for (int k = 0; k < 4; ++k)
                 if ((w >> (8 * k) & 0xFFu) && 4 * gi + k < n) bits |= 1u << k;
         }
-        const unsigned cntl = (unsigned)__popc(bits);
-        unsigned incl = cntl;  // inclusive warp scan of the per-lane counts
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (unsigned)o) incl += t;
-        }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (!total) continue;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&cnt->n_lit, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        unsigned p = base + incl - cntl;
+        unsigned p = block_alloc((unsigned)__popc(bits), &cnt->n_lit);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (bits >> k & 1u) lit_list[p++] = 4 * gi + k;
@@ -687,15 +740,8 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
         }
         if (!CONT) continue;
         // append the continuation rays: warp scan over "emits >= 1 / 2 / 3 rays"
-        unsigned b1 = __ballot_sync(0xffffffffu, n_emit >= 1);
-        unsigned b2 = CONDUCTOR ? 0u : __ballot_sync(0xffffffffu, n_emit >= 2), b3 = CONDUCTOR ? 0u : __ballot_sync(0xffffffffu, n_emit >= 3);
-        unsigned total = (unsigned)(__popc(b1) + __popc(b2) + __popc(b3));
-        unsigned base = 0;
-        if (lane == 0 && total) base = atomicAdd(&cnt->n_next, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned p = block_alloc((unsigned)n_emit, &cnt->n_next);
         if (n_emit > 0) {
-            unsigned lt = lanemask_lt();
-            unsigned p = base + (unsigned)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt));
             for (int k = 0; k < n_emit; ++k) {
                 qo.o[p + k] = make_float4(e_o[k].x, e_o[k].y, e_o[k].z, __uint_as_float(rs.pixel));
                 qo.d[p + k] = make_float4(e_d[k].x, e_d[k].y, e_d[k].z, __uint_as_float(rs.sample));
