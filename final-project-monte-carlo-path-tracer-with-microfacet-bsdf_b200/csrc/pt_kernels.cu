@@ -1258,7 +1258,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     free_scene(ctx);
     PackedScene packed;
     pack_scene(d, packed);
-    ctx->scene_bufs.resize(22);
+    ctx->scene_bufs.resize(23);
     auto up = [&](int slot, const void *src, size_t bytes) -> void * {
         if (upload(ctx, ctx->scene_bufs[slot], src, bytes)) return nullptr;
         return ctx->scene_bufs[slot].p;
@@ -1288,6 +1288,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_entries, const float4 *, 19, packed.lt_entries.data(), 16 * packed.lt_entries.size());
     UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
+    UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;

@@ -68,6 +68,15 @@ PT_HD uint32_t f2u(float f) {
     return c.u;
 #endif
 }
+PT_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c;
+    c.u = u;
+    return c.f;
+#endif
+}
 PT_HD f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 PT_HD float comp(f3 v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
 
@@ -193,6 +202,7 @@ struct SceneView {
     const float4 *nodes_ref;  // the reference's own topology (src/BVH.cpp:27-93), same layout: used by rays whose slab
                               // products can be NaN (see ray_needs_reference_tree) and by the parity entry points
     const float4 *v0, *e1, *e2, *nrm;  // per primitive
+    const float4 *tri;                 // per primitive, interleaved (v0, e1, e2): the three loads of a primitive test hit one or two lines
     const float *v1v2, *uv;            // 6 floats per primitive
     const uint32_t *prim_mat, *prim_kind;
     const Material *mats;
@@ -324,10 +334,11 @@ PT_HD float prune_bound(double best) {
 
 // primitive test of a leaf: Triangle::getIntersection or Sphere::getIntersection
 PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
-    float4 a = PT_LDG4(S.v0 + prim);
-    float4 b = PT_LDG4(S.e1 + prim);
+    const float4 *q = S.tri + 3 * (size_t)prim;
+    float4 a = PT_LDG4(q);
+    float4 b = PT_LDG4(q + 1);
     if (kind == NODE_TRIANGLE) {
-        float4 c = PT_LDG4(S.e2 + prim);
+        float4 c = PT_LDG4(q + 2);
         double u, v;
         return tri_hit(xyz(a), xyz(b), xyz(c), r, t, &u, &v);
     }
@@ -337,10 +348,6 @@ PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray 
     return ok;
 }
 
-// nodes[0] is the root and nodes[1] an EMPTY filler, so the walk starts at sibling pair 0.
-// The walk is written as a state machine (begin / step) so that the persistent traversal kernels can
-// interleave the walks of a warp's lanes and hand a finished lane a new ray; closest_hit() below is
-// the plain loop over the same steps.
 // The traversal tree may be any tree over the reference's leaf boxes (pt_build.hpp explains why the hits are the same)
 // as long as no slab product (p - o) * inv is NaN.  NaN needs an infinite inverse direction component (a zero or
 // denormal direction component) or a non-finite origin: those rays walk the reference's own topology instead.
@@ -355,8 +362,7 @@ struct Trav {
     float bound;
     uint32_t pair;
     int sp;
-    uint32_t stk[kStackSize];
-    float stk_t[kStackSize];
+    uint2 stk[kStackSize];  // (sibling pair index, box entry distance as bits): one 64-bit local access per push / pop
 };
 PT_HD void trav_begin(const SceneView &S, const Ray &r, Trav &T) {
     T.nodes = ray_needs_reference_tree(r) ? S.nodes_ref : S.nodes;
@@ -397,8 +403,7 @@ PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
     if (hr && tr > T.bound) hr = false;
     if (hl && hr) {
         bool left_near = !(tr < tl);
-        T.stk[T.sp] = left_near ? ra : la;
-        T.stk_t[T.sp] = left_near ? tr : tl;
+        T.stk[T.sp] = make_uint2(left_near ? ra : la, f2u(left_near ? tr : tl));
         T.sp++;
         T.pair = left_near ? la : ra;
         return true;
@@ -407,7 +412,8 @@ PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
     if (hr) { T.pair = ra; return true; }
     while (T.sp > 0) {
         --T.sp;
-        if (!(T.stk_t[T.sp] > T.bound)) { T.pair = T.stk[T.sp]; return true; }
+        const uint2 e = T.stk[T.sp];
+        if (!(u2f(e.y) > T.bound)) { T.pair = e.x; return true; }
     }
     return false;
 }

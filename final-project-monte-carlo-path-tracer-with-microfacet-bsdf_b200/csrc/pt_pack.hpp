@@ -22,6 +22,7 @@ struct PackedScene {
     // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
     // Entry = (bmin, prim id) (bmax, kind): the primitive's own reference leaf box, tested before the primitive.
+    std::vector<float4> tri;  // (v0, e1, e2) per primitive, interleaved
     std::vector<float4> lt_entries;
     std::vector<int> lt_off, lt_cnt;  // cnt < 0: too many neighbours, the window is searched by traversal instead
 };
@@ -58,6 +59,12 @@ inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
 }
 
 inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fast_tree = true) {
+    out.tri.resize(3 * (size_t)d->n_prims);
+    for (size_t i = 0; i < d->n_prims; ++i) {
+        std::memcpy(&out.tri[3 * i], d->prim_v0 + 4 * i, 16);
+        std::memcpy(&out.tri[3 * i + 1], d->prim_e1 + 4 * i, 16);
+        std::memcpy(&out.tri[3 * i + 2], d->prim_e2 + 4 * i, 16);
+    }
     out.nodes_ref.assign(d->nodes, d->nodes + d->n_nodes);
     for (auto &n : out.nodes_ref)
         if (n.kind == B2PT_NODE_EMPTY)

@@ -54,6 +54,7 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast) {
     v.mats = h->packed.mats.data();
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
     v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
+    v.tri = h->packed.tri.data();
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height; v.env = h->packed.env.data();
     for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
