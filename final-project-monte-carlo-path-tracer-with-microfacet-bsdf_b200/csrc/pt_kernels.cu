@@ -2,14 +2,19 @@
 //
 // Replaces the OpenMP pixel loop of Renderer::Render (src/Renderer.cpp:36-92) and everything
 // below it (Scene::castRay, src/Scene.cpp:85-184).  The recursion of castRay is unrolled into
-// waves of rays that move through five kernels per bounce:
+// a queue of rays that moves through these kernels once per bounce:
 //
-//   generate   camera rays of a wave of pixel-samples                 (Renderer.cpp:39-76)
-//   extend     closest hit of every queued ray                        (Scene::intersect)
-//   light      next-event shadow rays of every surviving vertex       (Scene::directLighting, ray part)
-//   shadow     visibility of every shadow ray                         (Scene.cpp:72-75)
-//   shade      the rest of castRay for one vertex: terminal cases, microfacet normal, Fresnel,
-//              direct light, Russian roulette, reflect/refract choice, continuation rays
+//   generate   tops the queue up with camera rays (path regeneration)   (Renderer.cpp:39-76)
+//   extend     closest hit of every queued ray                          (Scene::intersect)
+//   light      files every ray under terminal / material type x survives-roulette; one record per vertex
+//   nee        one lane per light sample: draws it, answers the "hit within EPSILON of dist" half of
+//              the visibility test from the light neighbourhood table, queues the rest as shadow rays
+//   shadow     occluder search for the queued shadow rays               (Scene.cpp:72-75)
+//   lit        compacts the accepted samples
+//   nee_eval   one lane per accepted sample: the direct-light summand   (Scene.cpp:76-79)
+//   terminal   rays that missed or hit an emitter                       (Scene.cpp:88-107,145-148)
+//   shade<T,C> the rest of castRay for one vertex on material type T: microfacet normal, Fresnel,
+//              sum of the direct-light terms, and (C) reflect/refract choice + continuation rays
 //
 // A queued ray carries up to three wavelength paths (R, G, B: Renderer.cpp:77-79) that still
 // share their geometry; they read the same sample stream, so they stay together until a
@@ -18,8 +23,9 @@
 // clamps of castRay (Scene.cpp:180-183) are carried as a clamped-affine map per path
 //  instead of a recursion stack.
 //
-// Queues are SoA float4 arrays compacted with __ballot_sync/__popc warp scans; counts stay on
-// the device, the host reads one counter per bounce to know when a wave has drained.
+// Queues are SoA float4 arrays; appends are combined per block in shared memory (ballot/popc
+// and shuffle scans inside the warp) so each block issues one atomic per counter.  Counts stay
+// on the device; the host reads one 16-byte counter per bounce to size the next launch.
 // There is no CPU path in this library.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
