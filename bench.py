@@ -380,6 +380,20 @@ def run_ours(args):
         except Exception:
             pass
         if world == 1 and not args.no_cpu_baseline and S.have_ref():
+            # RMSE vs the CPU reference (the metric's third part): the reference's own castRay replayed on the sample streams the
+            # GPU used, for a pixel subset of the frame (same scene, same camera, 8 spp) — outside every timed region
+            try:
+                ref = S.Ref(sc, env_png)
+                px = np.random.RandomState(0).choice(pix, 512, replace=False).astype(np.int32)
+                g, _ = ctx.render_samples(cam, px, 0, 8)
+                r = ref.render_samples(px, 0, 8)
+                ref.close()
+                gm, rm = g.mean(1), r.mean(1)
+                line["rmse_vs_cpu_ref"] = {"rmse": float(np.sqrt(np.mean((gm - rm) ** 2))), "mean_radiance": float(rm.mean()),
+                                           "max_abs_diff_per_sample": float(np.abs(g - r).max()), "pixels": 512, "spp": 8,
+                                           "how": "same sample streams on both sides (Philox keyed by pixel, sample)"}
+            except Exception as e:  # the checker is optional: never fail the bench line over it
+                line["rmse_vs_cpu_ref"] = {"error": str(e)[:200]}
             times, paths, cpu_rays = cpu_reference_run(sc, env_png, args.cpu_sample_spp, line["rays_per_path"])
             tt = sum(times) / len(times)
             line["cpu_baseline"] = {
