@@ -29,14 +29,24 @@ inline BuildBox box_empty_b() { return BuildBox{{INFINITY, INFINITY, INFINITY}, 
 inline void box_grow(BuildBox &a, const BuildBox &b) {
     for (int k = 0; k < 3; ++k) { a.mn[k] = std::fmin(a.mn[k], b.mn[k]); a.mx[k] = std::fmax(a.mx[k], b.mx[k]); }
 }
-inline float box_half_area(const BuildBox &b) {
+// Half surface area weighted per face normal: w[k] multiplies the face perpendicular to axis k.  With w = (1,1,1) this
+// is the isotropic surface-area heuristic; other weights are the expected |direction component| of a ray population
+// (the chance that such a ray crosses a box is proportional to the box's area projected along the ray).
+inline float box_half_area(const BuildBox &b, const float *w) {
     float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
     if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.f;
-    return dx * dy + dy * dz + dz * dx;
+    return w[2] * (dx * dy) + w[0] * (dy * dz) + w[1] * (dz * dx);
 }
 
+struct BuildOptions {
+    int bins = 16;
+    float w[3] = {1.f, 1.f, 1.f};
+};
+
 struct SahBuilder {
-    static constexpr int kBins = 16;
+    static constexpr int kMaxBins = 64;
+    int kBins = 16;
+    float w[3] = {1.f, 1.f, 1.f};  // face weights of the area measure (see box_half_area)
     static constexpr int kMaxDepth = 34;  // below this depth the builder falls back to median splits (stack bound)
     struct Leaf {
         BuildBox box;
@@ -46,6 +56,10 @@ struct SahBuilder {
     std::vector<Leaf> leaves;
     std::vector<b2pt_node> out;
     int max_depth = 0;
+    void configure(const BuildOptions &o) {
+        kBins = std::min(kMaxBins, std::max(2, o.bins));
+        for (int k = 0; k < 3; ++k) w[k] = o.w[k];
+    }
 
     // Leaf boxes are taken from the reference-topology leaves: exactly the boxes the reference tests.
     void collect(const b2pt_scene_desc *d) {
@@ -93,8 +107,8 @@ struct SahBuilder {
             for (int axis = 0; axis < 3; ++axis) {
                 float lo = cb.mn[axis], ext = cb.mx[axis] - lo;
                 if (!(ext > 0)) continue;
-                BuildBox bb[kBins];
-                size_t cnt[kBins];
+                BuildBox bb[kMaxBins];
+                size_t cnt[kMaxBins];
                 for (int b = 0; b < kBins; ++b) { bb[b] = box_empty_b(); cnt[b] = 0; }
                 float scale = kBins / ext;
                 for (size_t i = begin; i < end; ++i) {
@@ -102,18 +116,18 @@ struct SahBuilder {
                     box_grow(bb[b], leaves[i].box);
                     cnt[b]++;
                 }
-                float right_area[kBins];
-                size_t right_cnt[kBins];
+                float right_area[kMaxBins];
+                size_t right_cnt[kMaxBins];
                 BuildBox acc = box_empty_b();
                 size_t c = 0;
-                for (int b = kBins - 1; b > 0; --b) { box_grow(acc, bb[b]); c += cnt[b]; right_area[b] = box_half_area(acc); right_cnt[b] = c; }
+                for (int b = kBins - 1; b > 0; --b) { box_grow(acc, bb[b]); c += cnt[b]; right_area[b] = box_half_area(acc, w); right_cnt[b] = c; }
                 acc = box_empty_b();
                 c = 0;
                 for (int b = 0; b < kBins - 1; ++b) {
                     box_grow(acc, bb[b]);
                     c += cnt[b];
                     if (c == 0 || right_cnt[b + 1] == 0) continue;
-                    float cost = box_half_area(acc) * (float)c + right_area[b + 1] * (float)right_cnt[b + 1];
+                    float cost = box_half_area(acc, w) * (float)c + right_area[b + 1] * (float)right_cnt[b + 1];
                     if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
                 }
             }
@@ -150,6 +164,85 @@ struct SahBuilder {
         max_depth = 0;
         alloc_pair();
         if (!leaves.empty()) build(0, 0, leaves.size(), 0);
+    }
+};
+
+// ---- four-wide collapse --------------------------------------------------------------------------------------------
+// Turns a binary sibling-pair tree into quads: quad q = nodes[4q .. 4q+3], the up-to-four nearest descendants of one
+// binary node (the child with the largest box is opened first); an interior child's `a` is the index of its own quad,
+// unused slots are EMPTY with NaN boxes; slot 0's kind word also holds the quad's leaf / sphere masks (bits 8-15).  The leaves (primitive ids and leaf boxes) are untouched, so the hits are the
+// same as with any other tree over them; a walk needs about half the steps of the binary tree, each step being one
+// 128-byte line, and the primitive tests of the (up to four) leaf children of a step run together.
+struct QuadTree {
+    std::vector<b2pt_node> nodes;  // 4 per quad, root = quad 0
+    int stack_need = 0;            // entries a depth-first walk can hold at once (<= sum over a path of interior children - 1)
+};
+inline float node_half_area(const b2pt_node &n) {
+    float dx = n.bmax[0] - n.bmin[0], dy = n.bmax[1] - n.bmin[1], dz = n.bmax[2] - n.bmin[2];
+    if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.f;
+    return dx * dy + dy * dz + dz * dx;
+}
+struct QuadCollapser {
+    const std::vector<b2pt_node> &bin;
+    QuadTree &qt;
+    QuadCollapser(const std::vector<b2pt_node> &b, QuadTree &q) : bin(b), qt(q) {}
+    int alloc_quad() {
+        b2pt_node e{};
+        e.kind = B2PT_NODE_EMPTY;
+        for (int k = 0; k < 3; ++k) { e.bmin[k] = NAN; e.bmax[k] = NAN; }
+        for (int i = 0; i < 4; ++i) qt.nodes.push_back(e);
+        return (int)qt.nodes.size() / 4 - 1;
+    }
+    // Fills quad q with the collapse of the binary slots in `kids` (1 or 2 to start with); returns its stack need.
+    int fill(int q, std::vector<uint32_t> kids) {
+        for (;;) {
+            if (kids.size() >= 4) break;
+            int best = -1;
+            float best_area = -1.f;
+            for (size_t i = 0; i < kids.size(); ++i) {
+                const b2pt_node &n = bin[kids[i]];
+                if (n.kind != B2PT_NODE_INTERIOR) continue;
+                float a = node_half_area(n);
+                if (a > best_area) { best_area = a; best = (int)i; }
+            }
+            if (best < 0) break;
+            uint32_t pair = bin[kids[best]].a;
+            kids[best] = 2 * pair;
+            kids.insert(kids.begin() + best + 1, 2 * pair + 1);
+        }
+        // EMPTY fillers of the binary tree (odd sibling of a single child) are dropped
+        kids.erase(std::remove_if(kids.begin(), kids.end(), [&](uint32_t s) { return bin[s].kind == B2PT_NODE_EMPTY; }), kids.end());
+        int n_int = 0, deepest = 0;
+        for (size_t i = 0; i < kids.size(); ++i) {
+            b2pt_node n = bin[kids[i]];
+            if (n.kind == B2PT_NODE_INTERIOR) {
+                ++n_int;
+                int cq = alloc_quad();
+                uint32_t pair = n.a;
+                n.a = (uint32_t)cq;
+                qt.nodes[4 * (size_t)q + i] = n;
+                deepest = std::max(deepest, fill(cq, {2 * pair, 2 * pair + 1}));
+            } else {
+                qt.nodes[4 * (size_t)q + i] = n;
+            }
+        }
+        // slot 0's kind word also carries the quad's leaf mask (bits 8-11) and sphere mask (bits 12-15), so a step needs
+        // one word instead of four to know which of the children that passed are primitives
+        uint32_t meta = 0;
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t k = qt.nodes[4 * (size_t)q + i].kind & 0xFFu;
+            if (k == B2PT_NODE_TRIANGLE || k == B2PT_NODE_SPHERE) meta |= 1u << i;
+            if (k == B2PT_NODE_SPHERE) meta |= 16u << i;
+        }
+        qt.nodes[4 * (size_t)q].kind |= meta << 8;
+        return (n_int > 0 ? n_int - 1 : 0) + deepest;
+    }
+    void run() {
+        qt.nodes.clear();
+        int q = alloc_quad();
+        if (bin.empty()) return;
+        if (bin[0].kind == B2PT_NODE_INTERIOR) qt.stack_need = fill(q, {2 * bin[0].a, 2 * bin[0].a + 1});
+        else qt.stack_need = fill(q, {0});
     }
 };
 

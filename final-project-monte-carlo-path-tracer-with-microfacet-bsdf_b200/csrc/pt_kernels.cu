@@ -261,10 +261,27 @@ __device__ __forceinline__ unsigned fetch_rays(Fetch &F, bool idle, unsigned n, 
 }
 
 #ifndef B2PT_TRAV_MIN_BLOCKS
-#define B2PT_TRAV_MIN_BLOCKS 10  // 48 registers: 10 blocks per SM (measured +2.6 % over 56 registers / 9 blocks; 12 and 16 spill too much)
+#define B2PT_TRAV_MIN_BLOCKS 9  // shadow kernel: 56 registers / 9 blocks per SM (measured: 10 blocks -1.5 %, 8 -0.8 %, 12 -4 %)
 #endif
+#ifndef B2PT_EXT_MIN_BLOCKS
+#define B2PT_EXT_MIN_BLOCKS 9  // the four-wide walk keeps four entry distances and four child indices live: 56 registers / 9 blocks (measured: 8 blocks -0.6 %, 10 -3.5 %)
+#endif
+// Rays whose slab products can be NaN (pt::ray_needs_reference_tree) — and every ray of a scene whose four-wide tree was not
+// built — take the whole binary walk out of line; they are rare, the call keeps the main loop's registers for the quad walk.
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
+__device__ __noinline__ void binary_walk(const SceneView &S, const Ray &r, Hit *h, TravStats *st) { *h = closest_hit<COUNT>(S, r, st); }
+template <bool COUNT>
+__device__ __noinline__ bool binary_visible(const SceneView &S, const Ray &r, float dist, int phase, TravStats *st) {
+    ShadowTrav T;
+    uint32_t T_stack[kStackSize];
+    T.stk = T_stack;
+    shadow_begin(S, r, T, dist, phase);
+    while (shadow_step<COUNT>(S, r, dist, T, st)) {}
+    return T.visible;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
                                                         const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
                                                         unsigned *__restrict__ next, int *__restrict__ hit_prim, float *__restrict__ hit_t,
                                                         Counters *cnt) {
@@ -275,9 +292,11 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) extend_kernel(Sc
     bool has = false, exhausted = false;
     unsigned idx = 0;
     Ray r;
-    Trav T;
+    Trav4 T;
+    uint2 T_stack[kStackSize4];
+    T.stk = T_stack;
     r.o = r.d = r.inv = mk3(0, 0, 0);
-    trav_begin(S, r, T);
+    trav4_begin(T);
     Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
@@ -286,16 +305,26 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) extend_kernel(Sc
                 idx = got;
                 float4 o = qo[idx], d = qd[idx];
                 r = make_ray(xyz(o), xyz(d));
-                trav_begin(S, r, T);
-                has = true;
                 refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                    Hit h;
+                    binary_walk<COUNT>(S, r, &h, &st);
+                    hit_prim[idx] = h.prim;
+                    hit_t[idx] = (float)h.t;
+                } else {
+                    trav4_begin(T);
+                    has = true;
+                }
             }
             exhausted = F.dry && F.lo >= F.hi;
         }
         unsigned act = __ballot_sync(0xffffffffu, has);
-        if (!act) break;
+        if (!act) {
+            if (exhausted) break;
+            continue;
+        }
         do {
-            if (has && !trav_step<COUNT>(S, r, T, &st)) {
+            if (has && !trav4_step<COUNT>(S, r, T, &st)) {
                 hit_prim[idx] = T.h.prim;
                 hit_t[idx] = (float)T.h.t;  // Ray::operator()(double t) converts t to float before use
                 has = false;
@@ -450,6 +479,66 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *
 }
 
 // ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
+#ifndef B2PT_SHADOW_WIDE
+#define B2PT_SHADOW_WIDE 0
+#endif
+#if B2PT_SHADOW_WIDE
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
+                                                        const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
+                                                        unsigned char *__restrict__ vis, Counters *cnt) {
+    const unsigned n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31u;
+    TravStats st{0, 0};
+    bool has = false, exhausted = false;
+    unsigned idx = 0, slot = 0;  // slot: where the decision goes (sh_base[vertex] + sample)
+    float dist = 0.f;
+    Ray r;
+    ShadowTrav4 T;
+    uint32_t T_stack[kStackSize4];
+    T.stk = T_stack;
+    r.o = r.d = r.inv = mk3(0, 0, 0);
+    shadow4_begin(T, 0.f, 2);
+    Fetch F = fetch_begin(n);
+    for (;;) {
+        if (!exhausted) {
+            const unsigned got = fetch_rays(F, !has, n, next, lane);
+            if (!has && got != 0xFFFFFFFFu) {
+                idx = got;
+                float4 o = sh_o[idx], d = sh_d[idx];
+                r = make_ray(xyz(o), xyz(d));
+                dist = o.w;
+                const uint32_t tag = __float_as_uint(d.w);
+                const int phase = (tag & 0x80000000u) ? 1 : 2;
+                slot = tag & 0x7FFFFFFFu;
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                    vis[slot] = binary_visible<COUNT>(S, r, dist, phase, &st) ? 1 : 0;
+                } else {
+                    shadow4_begin(T, dist, phase);
+                    has = true;
+                }
+            }
+            exhausted = F.dry && F.lo >= F.hi;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!act) {
+            if (exhausted) break;
+            continue;
+        }
+        do {
+            if (has && !shadow4_step<COUNT>(S, r, dist, T, &st)) {
+                vis[slot] = T.visible ? 1 : 0;
+                has = false;
+            }
+            act = __ballot_sync(0xffffffffu, has);
+        } while (act && (exhausted || __popc(act) > kRefillBelow));
+    }
+    if (COUNT) {
+        unsigned long long nodes = warp_sum((unsigned long long)st.nodes), prims = warp_sum((unsigned long long)st.prims);
+        if (lane == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
+    }
+}
+#else
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
                                                         const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
@@ -462,6 +551,8 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
     float dist = 0.f;
     Ray r;
     ShadowTrav T;
+    uint32_t T_stack[kStackSize];
+    T.stk = T_stack;
     r.o = r.d = r.inv = mk3(0, 0, 0);
     shadow_begin(S, r, T, 0.f);
     Fetch F = fetch_begin(n);
@@ -495,6 +586,7 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
         if (lane == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
     }
 }
+#endif
 
 // ---- lit: compacts the accepted light samples (vis == 1) of the bounce into a list -------------------------------------------
 __global__ void __launch_bounds__(kBlock) lit_kernel(const unsigned char *__restrict__ vis, const unsigned *__restrict__ n_ptr, int all_lit,
@@ -799,7 +891,7 @@ __global__ void k_intersect(SceneView S, const float *o, const float *d, long lo
     unsigned long long nodes = 0, prims = 0;
     if (i < n) {
         TravStats st{0, 0};
-        Hit h = closest_hit<COUNT>(S, make_ray(ld3(o, i), ld3(d, i)), &st);
+        Hit h = closest_hit4<COUNT>(S, make_ray(ld3(o, i), ld3(d, i)), &st);
         prim[i] = h.prim; t[i] = h.t;
         nodes = st.nodes; prims = st.prims;
     }
@@ -811,7 +903,11 @@ __global__ void k_intersect(SceneView S, const float *o, const float *d, long lo
 __global__ void k_shadow(SceneView S, const float *o, const float *d, const float *dist, long long n, int *visible) {
     BATCH_INDEX(n)
     TravStats st{0, 0};
+    #if B2PT_SHADOW_WIDE
+    visible[i] = light_visible4<false>(S, make_ray(ld3(o, i), ld3(d, i)), dist[i], &st) ? 1 : 0;
+#else
     visible[i] = light_visible<false>(S, make_ray(ld3(o, i), ld3(d, i)), dist[i], &st) ? 1 : 0;
+#endif
 }
 __global__ void k_tri(const float *v9, const float *o, const float *d, long long n, int *hit, double *t) {
     BATCH_INDEX(n)
@@ -1264,7 +1360,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     free_scene(ctx);
     PackedScene packed;
     pack_scene(d, packed);
-    ctx->scene_bufs.resize(23);
+    ctx->scene_bufs.resize(24);
     auto up = [&](int slot, const void *src, size_t bytes) -> void * {
         if (upload(ctx, ctx->scene_bufs[slot], src, bytes)) return nullptr;
         return ctx->scene_bufs[slot].p;
@@ -1295,6 +1391,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
     UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
+    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.nodes.data(), sizeof(b2pt_node) * packed.quads.nodes.size());
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;

@@ -38,6 +38,7 @@ namespace pt {
 constexpr float kEps = 1e-4f;                  // EPSILON, src/Renderer.cpp:15
 constexpr float kPi = 3.141592653589793f;      // M_PI redefined as float, src/global.hpp:8-9
 constexpr int kStackSize = 48;
+constexpr int kStackSize4 = 64;  // four-wide walk (pt_build.hpp QuadTree::stack_need must stay below it)
 
 enum { MAT_SMOOTH_CONDUCTOR = 0, MAT_ROUGH_CONDUCTOR = 1, MAT_SMOOTH_DIELECTRIC = 2, MAT_ROUGH_DIELECTRIC = 3 };
 enum { NODE_INTERIOR = 0, NODE_TRIANGLE = 1, NODE_SPHERE = 2, NODE_EMPTY = 3 };
@@ -199,6 +200,8 @@ struct Material {
 struct SceneView {
     const float4 *nodes;      // traversal tree built by pt_build.hpp (binned SAH over the reference's leaves); 2 float4 per node:
                               // (bmin, a) (bmax, kind); EMPTY nodes carry NaN boxes, which fail the box test by themselves
+    const float4 *nodes4;     // `nodes` collapsed four-wide (pt_build.hpp): 8 float4 per quad = one 128-byte line per step; null when the
+                              // collapse needs a deeper stack than kStackSize4 (then every ray takes the binary walk)
     const float4 *nodes_ref;  // the reference's own topology (src/BVH.cpp:27-93), same layout: used by rays whose slab
                               // products can be NaN (see ray_needs_reference_tree) and by the parity entry points
     const float4 *v0, *e1, *e2, *nrm;  // per primitive
@@ -362,7 +365,8 @@ struct Trav {
     float bound;
     uint32_t pair;
     int sp;
-    uint2 stk[kStackSize];  // (sibling pair index, box entry distance as bits): one 64-bit local access per push / pop
+    uint2 *stk;  // kStackSize entries owned by the caller, (sibling pair index, box entry distance as bits): one 64-bit local access per
+                 // push / pop.  A pointer, not a member array: an array indexed at run time would pin the whole struct in local memory
 };
 PT_HD void trav_begin(const SceneView &S, const Ray &r, Trav &T) {
     T.nodes = ray_needs_reference_tree(r) ? S.nodes_ref : S.nodes;
@@ -420,8 +424,102 @@ PT_HD bool trav_step(const SceneView &S, const Ray &r, Trav &T, TravStats *st) {
 template <bool COUNT>
 PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
     Trav T;
+    uint2 T_stack[kStackSize];
+    T.stk = T_stack;
     trav_begin(S, r, T);
     while (trav_step<COUNT>(S, r, T, st)) {}
+    return T.h;
+}
+
+// ---- the same walk over the four-wide tree ------------------------------------------------------------------------------
+// One step = one quad = one 128-byte line: four box tests, the primitive tests of the leaf children that passed (one
+// loop, so lanes with leaves in different slots test together), then the nearest interior child; the others go on the
+// stack with their entry distances.  Same box test, same primitive tests, same pruning margin and tie rule as above.
+struct Trav4 {
+    Hit h;
+    float bound;
+    uint32_t quad;
+    int sp;
+    uint2 *stk;  // kStackSize4 entries owned by the caller
+};
+PT_HD void trav4_begin(Trav4 &T) {
+    T.h.t = 1.7976931348623157e308;
+    T.h.prim = -1;
+    T.bound = INFINITY;
+    T.sp = 0;
+    T.quad = 0;
+}
+// first set bit of a 4-bit mask selects among four registers: predicated selects, no indexing (indexing would put the
+// values in local memory)
+PT_HD float pick4(unsigned m, float a, float b, float c, float d) { return (m & 1u) ? a : ((m & 2u) ? b : ((m & 4u) ? c : d)); }
+PT_HD uint32_t pick4u(unsigned m, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return (m & 1u) ? a : ((m & 2u) ? b : ((m & 4u) ? c : d)); }
+template <bool COUNT>
+PT_HD bool trav4_step(const SceneView &S, const Ray &r, Trav4 &T, TravStats *st) {
+    const float4 *p = S.nodes4 + 8 * (size_t)T.quad;
+    const float4 l0 = PT_LDG4(p), h0 = PT_LDG4(p + 1), l1 = PT_LDG4(p + 2), h1 = PT_LDG4(p + 3);
+    const float4 l2 = PT_LDG4(p + 4), h2 = PT_LDG4(p + 5), l3 = PT_LDG4(p + 6), h3 = PT_LDG4(p + 7);
+    if (COUNT) st->nodes += 4;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    const bool b0 = box_hit(xyz(l0), xyz(h0), r, &t0) && !(t0 > T.bound);
+    const bool b1 = box_hit(xyz(l1), xyz(h1), r, &t1) && !(t1 > T.bound);
+    const bool b2 = box_hit(xyz(l2), xyz(h2), r, &t2) && !(t2 > T.bound);
+    const bool b3 = box_hit(xyz(l3), xyz(h3), r, &t3) && !(t3 > T.bound);
+    const uint32_t a0 = f2u(l0.w), a1 = f2u(l1.w), a2 = f2u(l2.w), a3 = f2u(l3.w);
+    const unsigned meta = f2u(h0.w) >> 8;  // leaf mask (bits 0-3), sphere mask (bits 4-7)
+    unsigned hit = (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u);
+    unsigned lm = hit & meta & 15u;
+    if (lm) {
+        hit ^= lm;
+#pragma unroll 1
+        do {
+            const float tl = pick4(lm, t0, t1, t2, t3);
+            const uint32_t prim = pick4u(lm, a0, a1, a2, a3);
+            const unsigned low = lm & (0u - lm);
+            lm ^= low;
+            if (tl > T.bound) continue;
+            double t;
+            if (COUNT) st->prims++;
+            if (prim_hit(S, prim, ((meta >> 4) & low) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t) &&
+                (t < T.h.t || (t == T.h.t && (int)prim > T.h.prim))) {
+                T.h.t = t; T.h.prim = (int)prim; T.bound = prune_bound(t);
+            }
+        } while (lm);
+        // the bound may have tightened
+        hit &= (t0 > T.bound ? 0u : 1u) | (t1 > T.bound ? 0u : 2u) | (t2 > T.bound ? 0u : 4u) | (t3 > T.bound ? 0u : 8u);
+    }
+    if (hit) {
+        // nearest interior child next, the others on the stack
+        unsigned bm = hit & (0u - hit);
+        float tb = pick4(hit, t0, t1, t2, t3);
+        if ((hit & 2u) && t1 < tb) { bm = 2u; tb = t1; }
+        if ((hit & 4u) && t2 < tb) { bm = 4u; tb = t2; }
+        if ((hit & 8u) && t3 < tb) { bm = 8u; tb = t3; }
+        T.quad = pick4u(bm, a0, a1, a2, a3);
+        hit ^= bm;
+        if (hit) {
+            if (hit & 1u) T.stk[T.sp++] = make_uint2(a0, f2u(t0));
+            if (hit & 2u) T.stk[T.sp++] = make_uint2(a1, f2u(t1));
+            if (hit & 4u) T.stk[T.sp++] = make_uint2(a2, f2u(t2));
+            if (hit & 8u) T.stk[T.sp++] = make_uint2(a3, f2u(t3));
+        }
+        return true;
+    }
+    while (T.sp > 0) {
+        --T.sp;
+        const uint2 e = T.stk[T.sp];
+        if (!(u2f(e.y) > T.bound)) { T.quad = e.x; return true; }
+    }
+    return false;
+}
+// Scene::intersect: the four-wide walk, or the reference's own topology for the rays that need it
+template <bool COUNT>
+PT_HD Hit closest_hit4(const SceneView &S, const Ray &r, TravStats *st) {
+    if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) return closest_hit<COUNT>(S, r, st);
+    Trav4 T;
+    uint2 T_stack[kStackSize4];
+    T.stk = T_stack;
+    trav4_begin(T);
+    while (trav4_step<COUNT>(S, r, T, st)) {}
     return T.h;
 }
 
@@ -440,7 +538,7 @@ struct ShadowTrav {
     float lo, hi;
     uint32_t pair;
     int sp;
-    uint32_t stk[kStackSize];
+    uint32_t *stk;  // kStackSize entries owned by the caller
 };
 // (W) without a traversal: a witness lies within EPSILON of the sampled point, so it is the sampled triangle or one of the
 // few primitives listed next to it in the light neighbourhood table.  Each candidate's own leaf box is tested first, as
@@ -524,8 +622,99 @@ PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats
     int w = window_witness(S, r, dist, lnode);
     if (w == 0) return false;
     ShadowTrav T;
+    uint32_t T_stack[kStackSize];
+    T.stk = T_stack;
     shadow_begin(S, r, T, dist, w == 1 ? 2 : 1);
     while (shadow_step<COUNT>(S, r, dist, T, st)) {}
+    return T.visible;
+}
+
+// ---- the visibility walk over the four-wide tree -------------------------------------------------------------------------
+struct ShadowTrav4 {
+    bool visible;
+    int phase;  // 1: window search (W), 2: occluder search (O)
+    float lo, hi;
+    uint32_t quad;
+    int sp;
+    uint32_t *stk;  // kStackSize4 entries owned by the caller
+};
+PT_HD void shadow4_begin(ShadowTrav4 &T, float dist, int phase) {
+    T.visible = false;
+    const float m = 4e-3f + 1e-5f * dist;
+    T.lo = dist - m; T.hi = dist + m;
+    T.sp = 0;
+    T.quad = 0;
+    T.phase = phase;
+}
+// Returns false when the decision is known (T.visible).
+template <bool COUNT>
+PT_HD bool shadow4_step(const SceneView &S, const Ray &r, float dist, ShadowTrav4 &T, TravStats *st) {
+    const double eps = (double)kEps, dd = (double)dist;
+    const float4 *p = S.nodes4 + 8 * (size_t)T.quad;
+    const float4 l0 = PT_LDG4(p), h0 = PT_LDG4(p + 1), l1 = PT_LDG4(p + 2), h1 = PT_LDG4(p + 3);
+    const float4 l2 = PT_LDG4(p + 4), h2 = PT_LDG4(p + 5), l3 = PT_LDG4(p + 6), h3 = PT_LDG4(p + 7);
+    if (COUNT) st->nodes += 4;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    const float lo = T.phase == 1 ? T.lo : -INFINITY;  // phase 1: only boxes that overlap the window in t can hold a witness
+    const bool b0 = box_hit2(xyz(l0), xyz(h0), r, &t0, &x0) && !(t0 > T.hi) && !(x0 < lo);
+    const bool b1 = box_hit2(xyz(l1), xyz(h1), r, &t1, &x1) && !(t1 > T.hi) && !(x1 < lo);
+    const bool b2 = box_hit2(xyz(l2), xyz(h2), r, &t2, &x2) && !(t2 > T.hi) && !(x2 < lo);
+    const bool b3 = box_hit2(xyz(l3), xyz(h3), r, &t3, &x3) && !(t3 > T.hi) && !(x3 < lo);
+    const uint32_t a0 = f2u(l0.w), a1 = f2u(l1.w), a2 = f2u(l2.w), a3 = f2u(l3.w);
+    const unsigned meta = f2u(h0.w) >> 8;
+    unsigned hit = (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u);
+    unsigned lm = hit & meta & 15u;
+    hit ^= lm;
+#pragma unroll 1
+    while (lm) {
+        const uint32_t prim = pick4u(lm, a0, a1, a2, a3);
+        const unsigned low = lm & (0u - lm);
+        lm ^= low;
+        double t;
+        if (COUNT) st->prims++;
+        if (prim_hit(S, prim, ((meta >> 4) & low) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t)) {
+            const bool inside = fabs(t - dd) < eps;
+            if (T.phase == 1) {
+                if (inside) {  // W holds: restart as the occluder search
+                    T.phase = 2; T.sp = 0; T.quad = 0;
+                    return true;
+                }
+            } else if (!inside && t < dd) {  // a closer hit outside the window: the closest hit fails the test
+                T.visible = false;
+                return false;
+            }
+        }
+    }
+    if (hit) {
+        unsigned bm = hit & (0u - hit);
+        float tb = pick4(hit, t0, t1, t2, t3);
+        if ((hit & 2u) && t1 < tb) { bm = 2u; tb = t1; }
+        if ((hit & 4u) && t2 < tb) { bm = 4u; tb = t2; }
+        if ((hit & 8u) && t3 < tb) { bm = 8u; tb = t3; }
+        T.quad = pick4u(bm, a0, a1, a2, a3);
+        hit ^= bm;
+        if (hit) {
+            if (hit & 1u) T.stk[T.sp++] = a0;
+            if (hit & 2u) T.stk[T.sp++] = a1;
+            if (hit & 4u) T.stk[T.sp++] = a2;
+            if (hit & 8u) T.stk[T.sp++] = a3;
+        }
+        return true;
+    }
+    if (T.sp == 0) { T.visible = (T.phase == 2); return false; }
+    T.quad = T.stk[--T.sp];
+    return true;
+}
+template <bool COUNT>
+PT_HD bool light_visible4(const SceneView &S, const Ray &r, float dist, TravStats *st, int lnode = -1) {
+    if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) return light_visible<COUNT>(S, r, dist, st, lnode);
+    int w = window_witness(S, r, dist, lnode);
+    if (w == 0) return false;
+    ShadowTrav4 T;
+    uint32_t T_stack[kStackSize4];
+    T.stk = T_stack;
+    shadow4_begin(T, dist, w == 1 ? 2 : 1);
+    while (shadow4_step<COUNT>(S, r, dist, T, st)) {}
     return T.visible;
 }
 

@@ -19,6 +19,7 @@ struct PackedScene {
     std::vector<b2pt_node> nodes_ref;   // the reference's topology, EMPTY boxes rewritten to NaN
     std::vector<b2pt_node> nodes_fast;  // binned-SAH tree over the same leaves (pt_build.hpp)
     int fast_depth = 0;
+    QuadTree quads;                     // nodes_fast collapsed four-wide; empty when its stack need exceeds kStackSize4
     // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
     // Entry = (bmin, prim id) (bmax, kind): the primitive's own reference leaf box, tested before the primitive.
@@ -58,7 +59,7 @@ inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
     return true;
 }
 
-inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fast_tree = true) {
+inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fast_tree = true, const BuildOptions *opt = nullptr) {
     out.tri.resize(3 * (size_t)d->n_prims);
     for (size_t i = 0; i < d->n_prims; ++i) {
         std::memcpy(&out.tri[3 * i], d->prim_v0 + 4 * i, 16);
@@ -73,10 +74,13 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
     out.fast_depth = 0;
     if (build_fast_tree) {
         SahBuilder b;
+        if (opt) b.configure(*opt);
         b.run(d);
         if (b.max_depth + 2 < kStackSize) { out.nodes_fast.swap(b.out); out.fast_depth = b.max_depth; }
     }
     if (out.nodes_fast.empty()) { out.nodes_fast = out.nodes_ref; out.fast_depth = (int)d->max_depth; }
+    QuadCollapser(out.nodes_fast, out.quads).run();
+    if (out.quads.stack_need + 2 >= kStackSize4) out.quads.nodes.clear();
     {
         // leaf boxes by primitive id
         std::vector<BuildBox> pb(d->n_prims, box_empty_b());

@@ -16,7 +16,7 @@ using namespace pt;
 
 struct HcScene {
     PackedScene packed;
-    std::vector<float4> nodes, nodes_ref, v0, e1, e2, nrm;
+    std::vector<float4> nodes, nodes4, nodes_ref, v0, e1, e2, nrm;
     std::vector<float> v1v2, uv, light_area, ln_area;
     std::vector<uint32_t> prim_mat, prim_kind, light_root, light_mat;
     std::vector<int> ln_left, ln_right, ln_prim;
@@ -26,13 +26,15 @@ static inline f3 V(const float *p) { return mk3(p[0], p[1], p[2]); }
 
 extern "C" {
 
-static void *scene_new(const b2pt_scene_desc *d, bool fast) {
+static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *opt = nullptr) {
     std::string err;
     if (!validate_scene(d, err)) return nullptr;
     HcScene *h = new HcScene();
-    pack_scene(d, h->packed, fast);
+    pack_scene(d, h->packed, fast, opt);
     h->nodes.resize(2 * h->packed.nodes_fast.size());
     std::memcpy(h->nodes.data(), h->packed.nodes_fast.data(), sizeof(b2pt_node) * h->packed.nodes_fast.size());
+    h->nodes4.resize(2 * h->packed.quads.nodes.size());
+    if (!h->nodes4.empty()) std::memcpy(h->nodes4.data(), h->packed.quads.nodes.data(), sizeof(b2pt_node) * h->packed.quads.nodes.size());
     h->nodes_ref.resize(2 * h->packed.nodes_ref.size());
     std::memcpy(h->nodes_ref.data(), h->packed.nodes_ref.data(), sizeof(b2pt_node) * h->packed.nodes_ref.size());
     auto cp4 = [&](std::vector<float4> &dst, const float *src) { dst.resize(d->n_prims); std::memcpy(dst.data(), src, 16 * (size_t)d->n_prims); };
@@ -49,7 +51,7 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast) {
     h->ln_right.assign(d->light_node_right, d->light_node_right + d->n_light_nodes);
     h->ln_prim.assign(d->light_node_prim, d->light_node_prim + d->n_light_nodes);
     SceneView &v = h->view;
-    v.nodes = h->nodes.data(); v.nodes_ref = h->nodes_ref.data(); v.v0 = h->v0.data(); v.e1 = h->e1.data(); v.e2 = h->e2.data(); v.nrm = h->nrm.data();
+    v.nodes = h->nodes.data(); v.nodes4 = h->nodes4.empty() ? nullptr : h->nodes4.data(); v.nodes_ref = h->nodes_ref.data(); v.v0 = h->v0.data(); v.e1 = h->e1.data(); v.e2 = h->e2.data(); v.nrm = h->nrm.data();
     v.v1v2 = h->v1v2.data(); v.uv = h->uv.data(); v.prim_mat = h->prim_mat.data(); v.prim_kind = h->prim_kind.data();
     v.mats = h->packed.mats.data();
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
@@ -64,6 +66,61 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast) {
 // fast = 1: the library's traversal tree (pt_build.hpp); 0: the reference's topology only
 void *hc_scene_new2(const b2pt_scene_desc *d, int fast) { return scene_new(d, fast != 0); }
 void *hc_scene_new(const b2pt_scene_desc *d) { return scene_new(d, true); }
+// tree experiments (tools/tree_lab.py): builder options
+void *hc_scene_new_opts(const b2pt_scene_desc *d, int bins, float wx, float wy, float wz) {
+    BuildOptions o;
+    o.bins = bins; o.w[0] = wx; o.w[1] = wy; o.w[2] = wz;
+    return scene_new(d, true, &o);
+}
+void hc_intersect4(void *h, const float *o, const float *d, long n, int *prim, double *t, unsigned long long *counts) {
+    const SceneView &S = ((HcScene *)h)->view;
+    unsigned long long nodes = 0, prims = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, prims)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        Hit hit = closest_hit4<true>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), &st);
+        prim[i] = hit.prim; t[i] = hit.t;
+        nodes += st.nodes; prims += st.prims;
+    }
+    if (counts) { counts[0] = nodes; counts[1] = prims; }
+}
+int hc_quad_stack_need(void *h) { return ((HcScene *)h)->packed.quads.stack_need; }
+long hc_quad_count(void *h) { return (long)((HcScene *)h)->packed.quads.nodes.size() / 4; }
+void hc_occluder_counts4(void *h, const float *o, const float *d, const float *dist, long n, int *visible, unsigned long long *counts) {
+    const SceneView &S = ((HcScene *)h)->view;
+    unsigned long long nodes = 0, prims = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, prims)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
+        ShadowTrav4 T;
+        uint32_t T_stack[kStackSize4];
+        T.stk = T_stack;
+        shadow4_begin(T, dist[i], 2);
+        while (shadow4_step<true>(S, r, dist[i], T, &st)) {}
+        visible[i] = T.visible ? 1 : 0;
+        nodes += st.nodes; prims += st.prims;
+    }
+    counts[0] = nodes; counts[1] = prims;
+}
+// occluder searches (phase 2 only: the window is assumed to hold) with node / primitive-test counts
+void hc_occluder_counts(void *h, const float *o, const float *d, const float *dist, long n, int *visible, unsigned long long *counts) {
+    const SceneView &S = ((HcScene *)h)->view;
+    unsigned long long nodes = 0, prims = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, prims)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
+        ShadowTrav T;
+        uint32_t T_stack[kStackSize];
+        T.stk = T_stack;
+        shadow_begin(S, r, T, dist[i], 2);
+        while (shadow_step<true>(S, r, dist[i], T, &st)) {}
+        visible[i] = T.visible ? 1 : 0;
+        nodes += st.nodes; prims += st.prims;
+    }
+    counts[0] = nodes; counts[1] = prims;
+}
 int hc_fast_depth(void *h) { return ((HcScene *)h)->packed.fast_depth; }
 long hc_fast_nodes(void *h) { return (long)((HcScene *)h)->packed.nodes_fast.size(); }
 void hc_scene_free(void *h) { delete (HcScene *)h; }

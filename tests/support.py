@@ -297,13 +297,20 @@ class HostCheck:
             self.L.hc_scene_free(self.h)
             self.h = None
 
-    def intersect(self, o, d, counts=False):
+    def intersect(self, o, d, counts=False, binary=False):
+        """Closest hits as the extend kernel finds them: the four-wide walk (pt::closest_hit4), or with binary=True the
+        sibling-pair walk the shadow kernel and the degenerate rays use.  counts: (boxes tested, primitives tested)."""
         o, d = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
         prim = np.zeros(len(o), np.int32)
         t = np.zeros(len(o), np.float64)
         cnt = (C.c_ulonglong * 2)()
-        self.L.hc_intersect(self.h, fp(o), fp(d), C.c_long(len(o)), ip(prim), t.ctypes.data_as(c_double_p), cnt)
+        (self.L.hc_intersect if binary else self.L.hc_intersect4)(self.h, fp(o), fp(d), C.c_long(len(o)), ip(prim), t.ctypes.data_as(c_double_p), cnt)
         return (prim, t, (cnt[0], cnt[1])) if counts else (prim, t)
+
+    def quad_stats(self):
+        """(number of quads of the four-wide tree, stack entries its walk can need)."""
+        self.L.hc_quad_count.restype = C.c_long
+        return int(self.L.hc_quad_count(self.h)), int(self.L.hc_quad_stack_need(self.h))
 
     def shadow(self, o, d, dist):
         o, d, s = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3), f32(dist)

@@ -68,6 +68,20 @@ def test_scene_intersect_bit_exact(world):
     assert nodes > 0 and prims > 0
 
 
+def test_binary_and_four_wide_walks_agree(world):
+    """The sibling-pair walk (shadow kernel, degenerate rays) and the four-wide walk (extend kernel) over the same leaves
+    return the same hits bit for bit; the four-wide one needs about half the steps (one step = four boxes)."""
+    name, sc, ref, hc = world
+    o, d, _ = scenes.ray_batch(ref, sc, n_pixels=1500, samples=2, seed=5)
+    prim_b, t_b, (boxes_b, _) = hc.intersect(o, d, counts=True, binary=True)
+    prim_q, t_q, (boxes_q, _) = hc.intersect(o, d, counts=True)
+    assert np.array_equal(prim_b, prim_q) and np.array_equal(t_b.view(np.uint64), t_q.view(np.uint64))
+    quads, need = hc.quad_stats()
+    assert quads > 0 and need + 2 < 64
+    if name != "cornell":  # 35 primitives: nothing to collapse
+        assert boxes_q / 4 < 0.7 * boxes_b / 2, (boxes_q, boxes_b)
+
+
 def test_degenerate_rays_take_the_reference_tree(world):
     """Zero / denormal direction components and origins on box planes: slab products are NaN or infinite."""
     name, sc, ref, hc = world
