@@ -1004,6 +1004,12 @@ struct b2pt_ctx {
     cudaStream_t stream = nullptr;      // the stream all work is issued on
     cudaStream_t own_stream = nullptr;  // created by b2pt_create
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Side streams for the kernels of a bounce that do not depend on each other (terminal + the eight shade variants): they
+    // run next to each other, so their launch latencies and ramp-down tails overlap instead of adding up.
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[kSide] = {nullptr, nullptr, nullptr};
+    int n_side = kSide;  // 0: everything on the main stream (B2PT_SIDE_STREAMS=0)
     std::string err;
     bool has_scene = false;
     SceneView view{};
@@ -1141,10 +1147,19 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
                                              : (unsigned long long)job.n_pixels * (unsigned long long)p->sample_count;
     if (job.mode == 1 && total > 0xFFFFFFFFull / 3) return fail(ctx, B2PT_ERR_INVALID, "too many listed samples");
 
-    size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : (S.n_dir <= 8 ? (size_t)16 << 20 : (size_t)4 << 20);
+    // Queue target.  Every bounce costs a fixed ~0.15 ms (about twenty launches, their ramp-down tails, one host round trip)
+    // whatever the queue holds, so the queue is made as long as the memory allows: 48 Mi rays = 82 GB of wave state at four
+    // light samples per vertex (measured: 8 Mi 15.0, 16 Mi 15.9, 32 Mi 16.4, 48 Mi 16.6 Grays/s).  Halved until it fits when
+    // the device has less to give.
+    size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : (S.n_dir <= 8 ? (size_t)48 << 20 : (size_t)12 << 20);
     if (wave > total) wave = (size_t)std::max<unsigned long long>(total, 1);
     wave = (wave + kBlock - 1) / kBlock * kBlock;
     int r = setup_wave(ctx, wave * 3, S.n_dir);
+    while (r == B2PT_ERR_OOM && p->max_wave_bundles <= 0 && wave > ((size_t)1 << 20)) {
+        cudaGetLastError();
+        wave = (wave / 2 + kBlock - 1) / kBlock * kBlock;
+        r = setup_wave(ctx, wave * 3, S.n_dir);
+    }
     if (r) return r;
 
     cudaStream_t st = ctx->stream;
@@ -1183,6 +1198,11 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vtx_pn, ctx->wb.vtx_ps,
                                                            ctx->wb.vtx_ray, ctx->wb.lists, dc, gp.k0, gp.k1);
         launches++;
+        if (ctx->n_side > 0) {  // misses, emitters and probe misses need nothing from the light samples: alongside nee / shadow
+            CU(cudaEventRecord(ctx->fork_ev[1], st));
+            CU(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev[1], 0));
+            terminal_kernel<<<grid_for(n, ctx, 16), kBlock, 0, ctx->side[0]>>>(S, qa, ctx->wb.lists, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
+        }
         if (S.enable_shadow) {
             nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, ctx->wb.vtx_ps, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o,
                                                                                 ctx->wb.sh_d, dc, gp.k0, gp.k1);
@@ -1204,12 +1224,29 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             const unsigned g = grid_for(n, ctx, 16);
             const uint32_t *L = ctx->wb.lists;
             const size_t cap = qa.cap;
-            terminal_kernel<<<g, kBlock, 0, st>>>(S, qa, L, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
-#define SHADE(T, C) shade_kernel<T, C><<<g, kBlock, 0, st>>>(S, qa, qb, L + (size_t)(1 + 2 * T + (C ? 1 : 0)) * cap, &dc->n_class[1 + 2 * T + (C ? 1 : 0)], \
+            // terminal + shade variants read the same inputs and only append / accumulate with atomics: spread over the side streams
+            const int ns = ctx->n_side;
+            cudaStream_t lanes[1 + b2pt_ctx::kSide];
+            lanes[0] = st;
+            for (int k = 0; k < ns; ++k) lanes[1 + k] = ctx->side[k];
+            if (ns > 0) {
+                CU(cudaEventRecord(ctx->fork_ev[0], st));
+                for (int k = 0; k < ns; ++k) CU(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev[0], 0));
+            }
+            int turn = 0;
+            auto lane = [&]() { cudaStream_t q = lanes[turn % (1 + ns)]; ++turn; return q; };
+#define SHADE(T, C) shade_kernel<T, C><<<g, kBlock, 0, lane()>>>(S, qa, qb, L + (size_t)(1 + 2 * T + (C ? 1 : 0)) * cap, &dc->n_class[1 + 2 * T + (C ? 1 : 0)], \
                                                           ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vis, ctx->wb.nee_val, dc, sp)
-            SHADE(MAT_SMOOTH_CONDUCTOR, false); SHADE(MAT_SMOOTH_CONDUCTOR, true); SHADE(MAT_ROUGH_CONDUCTOR, false); SHADE(MAT_ROUGH_CONDUCTOR, true);
-            SHADE(MAT_SMOOTH_DIELECTRIC, false); SHADE(MAT_SMOOTH_DIELECTRIC, true); SHADE(MAT_ROUGH_DIELECTRIC, false); SHADE(MAT_ROUGH_DIELECTRIC, true);
+            // the long ones first, one per stream
+            SHADE(MAT_SMOOTH_DIELECTRIC, true); SHADE(MAT_SMOOTH_CONDUCTOR, true); SHADE(MAT_ROUGH_CONDUCTOR, true);
+            if (ns == 0) terminal_kernel<<<g, kBlock, 0, st>>>(S, qa, L, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
+            SHADE(MAT_SMOOTH_DIELECTRIC, false); SHADE(MAT_SMOOTH_CONDUCTOR, false); SHADE(MAT_ROUGH_CONDUCTOR, false);
+            SHADE(MAT_ROUGH_DIELECTRIC, true); SHADE(MAT_ROUGH_DIELECTRIC, false);
 #undef SHADE
+            for (int k = 0; k < ns; ++k) {
+                CU(cudaEventRecord(ctx->join_ev[k], ctx->side[k]));
+                CU(cudaStreamWaitEvent(st, ctx->join_ev[k], 0));
+            }
             swap_counts_kernel<<<1, 1, 0, st>>>(dc);
             launches += 10;
         }
@@ -1318,6 +1355,10 @@ int b2pt_create(b2pt_ctx **out, int device) {
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     c->stream = c->own_stream;
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    for (auto &sd : c->side) ok = ok && cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &ev : c->fork_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    for (auto &ev : c->join_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (const char *e = getenv("B2PT_SIDE_STREAMS")) c->n_side = std::max(0, std::min((int)b2pt_ctx::kSide, atoi(e)));
     ok = ok && cudaMalloc((void **)&c->d_cnt, sizeof(Counters)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)) == cudaSuccess;
     if (!ok) {
@@ -1339,6 +1380,9 @@ void b2pt_destroy(b2pt_ctx *c) {
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->fork_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->join_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &sd : c->side) if (sd) cudaStreamDestroy(sd);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
