@@ -68,6 +68,10 @@ struct Counters {
     unsigned int n_lit, pad1;                 // accepted light samples of this bounce
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
     unsigned int max_depth, pad2;
+    // Generation plan of the next bounce, written by plan_generation (one thread) so that the host never has to know the
+    // queue length: camera rays [gen_first, gen_first + gen_count) top the queue up to `wave`.
+    unsigned long long gen_first, gen_next, gen_total;
+    unsigned int gen_count, wave, waves, pad3;
 };
 
 // ---- ray queue (SoA) -----------------------------------------------------------------------------
@@ -163,7 +167,9 @@ __device__ __forceinline__ unsigned block_alloc(unsigned my_count, unsigned *cou
 // ---- generate: Renderer.cpp:39-76 -----------------------------------------------------------------------
 // Appends to queue `q`, whose length lives in *count (path regeneration: new camera rays top up the queue
 // every bounce, so the kernels keep working on full queues until the samples run out).
-__global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams gp, Queue q, unsigned *count) {
+__global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams gp, Queue q, const Counters *plan, unsigned *count) {
+    gp.first = plan->gen_first;  // read-only during this kernel (plan_generation ran before it)
+    gp.count = plan->gen_count;
     const unsigned long long rounded = ((unsigned long long)gp.count + kBlock - 1) / kBlock * kBlock;
     for (unsigned long long it = (unsigned long long)blockIdx.x * kBlock; it < rounded; it += (unsigned long long)gridDim.x * kBlock) {
         unsigned long long li = it + threadIdx.x;
@@ -865,6 +871,24 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
     }
 }
 
+__device__ void plan_generation(Counters *cnt) {
+    const unsigned n = cnt->n_cur;
+    unsigned g = 0;
+    if (cnt->gen_next < cnt->gen_total && n < cnt->wave) {
+        const unsigned long long left = cnt->gen_total - cnt->gen_next;
+        g = cnt->wave - n;
+        if ((unsigned long long)g > left) g = (unsigned)left;
+    }
+    cnt->gen_first = cnt->gen_next;
+    cnt->gen_count = g;
+    cnt->gen_next += g;
+    if (g) cnt->waves++;
+}
+__global__ void begin_counts_kernel(Counters *cnt, unsigned wave, unsigned long long total) {
+    cnt->wave = wave;
+    cnt->gen_total = total;
+    plan_generation(cnt);
+}
 __global__ void swap_counts_kernel(Counters *cnt) {
     cnt->rays_closest += cnt->n_cur;
     cnt->rays_shadow += cnt->n_shadow;
@@ -876,6 +900,7 @@ __global__ void swap_counts_kernel(Counters *cnt) {
     cnt->fetch_extend = 0;
     cnt->fetch_shadow = 0;
     cnt->n_lit = 0;
+    plan_generation(cnt);
 }
 
 // ---- batch kernels for the parity entry points ---------------------------------------------------------------
@@ -1024,6 +1049,9 @@ struct b2pt_ctx {
     WaveBufs wb{};
     Counters *d_cnt = nullptr;
     Counters *h_cnt = nullptr;  // pinned
+    Counters *h_ring = nullptr; // pinned, two entries: the counters of the last two bounces (the host runs one bounce ahead)
+    cudaEvent_t done_ev[2] = {nullptr, nullptr};
+    cudaEvent_t tev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // extend / shadow timing per ring slot
     DevBuf fb;                  // device accumulation buffer of b2pt_render / b2pt_render_samples
     DevBuf pixels;
     std::vector<DevBuf> scratch;
@@ -1168,32 +1196,31 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     ShadeParams sp{gp.k0, gp.k1, (float)p->spp_total, job.d_acc};
     double extend_ms = 0, shadow_ms = 0;
     unsigned long long launches = 0, ext_launches = 0, sh_launches = 0;
-    unsigned waves = 0;
     Counters *dc = ctx->d_cnt;
     // Path regeneration: every bounce the queue is topped up with new camera rays to `wave` entries, so all kernels work
     // on full queues until the samples run out; only the end of the call sees the thin tail of deep paths.
-    unsigned long long next_first = 0;
-    size_t n = 0;  // length of the current queue as known to the host
-    int cur = 0;
-    for (;;) {
-        Queue &qa = ctx->wb.q[cur], &qb = ctx->wb.q[cur ^ 1];
-        size_t gen = 0;
-        if (next_first < total && n < wave) {
-            gen = (size_t)std::min<unsigned long long>(wave - n, total - next_first);
-            gp.first = next_first;
-            gp.count = (unsigned)gen;
-            generate_kernel<<<grid_for(gen, ctx, 16), kBlock, 0, st>>>(dcam, gp, qa, &dc->n_cur);
-            next_first += gen;
-            launches++;
-            waves++;
-        }
-        n += gen * (split ? 3 : 1);  // upper bound (tiles overhang the image edges)
-        if (n == 0) break;
-        if (n > ctx->wave_rays) return fail(ctx, B2PT_ERR_CUDA, "ray queue overflow (internal error)");
-        CU(cudaEventRecord(ctx->ev[2], st));
+    // The plan of each top-up is made on the device (plan_generation), so the host does not need the queue length to issue
+    // a bounce: it runs ONE BOUNCE AHEAD of the counters it reads back (bounce k is in the stream before the counters of
+    // bounce k-1 are waited for), and the GPU never idles through a host round trip.  The price is one empty bounce at the
+    // end of a call.  Launch grids are sized from a bound: a queue cannot grow beyond three times its length (a ray carries
+    // at most three wavelength paths, each emits at most one ray) plus what is generated.
+    const int per = split ? 3 : 1;
+    begin_counts_kernel<<<1, 1, 0, st>>>(dc, (unsigned)wave, total);
+    launches++;
+    size_t len_prev = 0;          // rays processed by the last bounce whose counters have been read
+    bool gen_open = total > 0;    // camera rays may still be generated
+    for (unsigned k = 0; total > 0; ++k) {
+        const int ring = (int)(k & 1u);
+        Queue &qa = ctx->wb.q[ring], &qb = ctx->wb.q[ring ^ 1];
+        // bound on this bounce's queue length (two bounces may have passed since len_prev was read)
+        size_t n = std::min<size_t>(ctx->wave_rays, 9 * len_prev + (gen_open || k < 2 ? 2 * wave * (size_t)per : 0));
+        if (n == 0) n = 1;
+        generate_kernel<<<grid_for(gen_open || k < 2 ? wave : 1, ctx, 16), kBlock, 0, st>>>(dcam, gp, qa, dc, &dc->n_cur);
+        launches++;
+        CU(cudaEventRecord(ctx->tev[ring][0], st));
         if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
         else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
-        CU(cudaEventRecord(ctx->ev[3], st));
+        CU(cudaEventRecord(ctx->tev[ring][1], st));
         launches++; ext_launches++;
         light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vtx_pn, ctx->wb.vtx_ps,
                                                            ctx->wb.vtx_ray, ctx->wb.lists, dc, gp.k0, gp.k1);
@@ -1207,10 +1234,10 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, ctx->wb.vtx_ps, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o,
                                                                                 ctx->wb.sh_d, dc, gp.k0, gp.k1);
             launches++;
-            CU(cudaEventRecord(ctx->ev[4], st));
+            CU(cudaEventRecord(ctx->tev[ring][2], st));
             if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
             else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
-            CU(cudaEventRecord(ctx->ev[5], st));
+            CU(cudaEventRecord(ctx->tev[ring][3], st));
             launches++; sh_launches++;
         }
         {
@@ -1228,10 +1255,10 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             const int ns = ctx->n_side;
             cudaStream_t lanes[1 + b2pt_ctx::kSide];
             lanes[0] = st;
-            for (int k = 0; k < ns; ++k) lanes[1 + k] = ctx->side[k];
+            for (int j = 0; j < ns; ++j) lanes[1 + j] = ctx->side[j];
             if (ns > 0) {
                 CU(cudaEventRecord(ctx->fork_ev[0], st));
-                for (int k = 0; k < ns; ++k) CU(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev[0], 0));
+                for (int j = 0; j < ns; ++j) CU(cudaStreamWaitEvent(ctx->side[j], ctx->fork_ev[0], 0));
             }
             int turn = 0;
             auto lane = [&]() { cudaStream_t q = lanes[turn % (1 + ns)]; ++turn; return q; };
@@ -1243,24 +1270,38 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             SHADE(MAT_SMOOTH_DIELECTRIC, false); SHADE(MAT_SMOOTH_CONDUCTOR, false); SHADE(MAT_ROUGH_CONDUCTOR, false);
             SHADE(MAT_ROUGH_DIELECTRIC, true); SHADE(MAT_ROUGH_DIELECTRIC, false);
 #undef SHADE
-            for (int k = 0; k < ns; ++k) {
-                CU(cudaEventRecord(ctx->join_ev[k], ctx->side[k]));
-                CU(cudaStreamWaitEvent(st, ctx->join_ev[k], 0));
+            for (int j = 0; j < ns; ++j) {
+                CU(cudaEventRecord(ctx->join_ev[j], ctx->side[j]));
+                CU(cudaStreamWaitEvent(st, ctx->join_ev[j], 0));
             }
             swap_counts_kernel<<<1, 1, 0, st>>>(dc);
             launches += 10;
         }
-        cur ^= 1;
-        CU(cudaMemcpyAsync(ctx->h_cnt, dc, 16, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        // counters after this bounce: (n_cur = the next queue before its top-up, gen_count = the top-up planned for it)
+        CU(cudaMemcpyAsync(&ctx->h_ring[ring], dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->done_ev[ring], st));
+        if (k == 0) continue;
+        // wait for the bounce before this one
+        const int prev = ring ^ 1;
+        CU(cudaEventSynchronize(ctx->done_ev[prev]));
         CU(cudaGetLastError());
-        n = ctx->h_cnt->n_cur;
+        const Counters &h = ctx->h_ring[prev];
         if (stats) {
             float ms = 0;
-            CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+            CU(cudaEventElapsedTime(&ms, ctx->tev[prev][0], ctx->tev[prev][1]));
             extend_ms += ms;
-            if (S.enable_shadow) { CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); shadow_ms += ms; }
+            if (S.enable_shadow) { CU(cudaEventElapsedTime(&ms, ctx->tev[prev][2], ctx->tev[prev][3])); shadow_ms += ms; }
         }
+        // after bounce k-1 the queue of bounce k held n_cur rays and gen_count bundles were planned for it
+        const size_t len_k = (size_t)h.n_cur + (size_t)h.gen_count * (size_t)per;
+        if (len_k > ctx->wave_rays) return fail(ctx, B2PT_ERR_CUDA, "ray queue overflow (internal error)");
+        gen_open = h.gen_next < total;
+        len_prev = len_k;
+        if (len_k == 0) break;  // bounce k (already issued) is empty: nothing is left in flight
+    }
+    if (total > 0) {  // the last bounce issued
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
     }
     CU(cudaEventRecord(ctx->ev[1], st));
     CU(cudaMemcpyAsync(ctx->h_cnt, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -1280,7 +1321,7 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         stats->nodes_fetched = h.nodes + h.sh_nodes; stats->prims_tested = h.prims + h.sh_prims;
         stats->extend_nodes = h.nodes; stats->extend_prims = h.prims; stats->shadow_nodes = h.sh_nodes; stats->shadow_prims = h.sh_prims;
         stats->vertices_shaded = h.vertices;
-        stats->max_depth = h.max_depth; stats->waves = waves;
+        stats->max_depth = h.max_depth; stats->waves = h.waves;
     }
     return B2PT_OK;
 }
@@ -1361,6 +1402,9 @@ int b2pt_create(b2pt_ctx **out, int device) {
     if (const char *e = getenv("B2PT_SIDE_STREAMS")) c->n_side = std::max(0, std::min((int)b2pt_ctx::kSide, atoi(e)));
     ok = ok && cudaMalloc((void **)&c->d_cnt, sizeof(Counters)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&c->h_ring, 2 * sizeof(Counters)) == cudaSuccess;
+    for (auto &ev : c->done_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    for (auto &row : c->tev) for (auto &ev : row) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     if (!ok) {
         std::string msg = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         b2pt_destroy(c);
@@ -1379,6 +1423,9 @@ void b2pt_destroy(b2pt_ctx *c) {
     for (auto &b : c->scratch) release(b);
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
+    for (auto &ev : c->done_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &row : c->tev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->fork_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->join_ev) if (ev) cudaEventDestroy(ev);
