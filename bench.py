@@ -338,6 +338,10 @@ def run_ours(args):
         ext_launch_ms = ext_ms / max(ext_launches, 1)
         achieved = (rays_closest / max(ext_launches, 1)) * bytes_per_ray / (ext_launch_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         sh_achieved = rays_shadow * sh_bytes_per_ray / (sh_ms * 1e-3) / 1e9 if sh_ms > 0 else 0.0
+        try:  # the scene is cache-resident: the bandwidth that can bound the walk is the L2's, measured here (outside the timed region)
+            l2_gbs = ctx.measure_l2_read_gbs()
+        except Exception:
+            l2_gbs = None
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture (per ray x rays of an average launch)
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["extend_kernel"]
@@ -363,7 +367,10 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "extend_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "algorithmic bytes are served by L1/L2 (the scene is cache-resident); DRAM traffic is the 45 B/ray of queue records",
+                         "note": "algorithmic bytes are served by L1/L2 (the scene is cache-resident), so frac can exceed 1; DRAM traffic is the "
+                                 "45 B/ray of queue records; ncu (profiles/): the walk is bound by the L1 data pipe and issue slots",
+                         "l2": {"peak": l2_gbs, "frac": (achieved / l2_gbs) if l2_gbs else None, "unit": "GB/s",
+                                "how": "b2pt_measure_l2_read_gbs: 64 passes of LDG.128 over a 32 MiB buffer, slices rotated between SMs"},
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": st_count.extend_nodes / ext_rays,
                          "tris_per_ray": st_count.extend_prims / ext_rays, "avg_launch_ms": ext_launch_ms,
                          "share_of_step": ext_ms / gpu_ms if gpu_ms else None,

@@ -214,6 +214,7 @@ def gpu_lib():
         L.b2pt_stream_uniforms.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32,
                                            c_float_p]
         L.b2pt_measure_copy_gbs.argtypes = [C.c_void_p, C.c_size_t, C.c_int, c_double_p]
+        L.b2pt_measure_l2_read_gbs.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, c_double_p]
         _gpu = L
     return _gpu
 
@@ -559,6 +560,12 @@ class Context:
     def measure_copy_gbs(self, nbytes=1 << 30, iters=10):
         g = C.c_double()
         self._ck(self.L.b2pt_measure_copy_gbs(self.h, nbytes, iters, C.byref(g)))
+        return g.value
+
+    def measure_l2_read_gbs(self, nbytes=32 << 20, repeats=64, iters=5):
+        """Read bandwidth out of the L2 (GB/s): the denominator for traversal kernels whose tree is cache-resident."""
+        g = C.c_double()
+        self._ck(self.L.b2pt_measure_l2_read_gbs(self.h, nbytes, repeats, iters, C.byref(g)))
         return g.value
 
 

@@ -1015,6 +1015,23 @@ __global__ void k_copy(const float4 *__restrict__ a, float4 *__restrict__ b, siz
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
 
+// Read-only streaming over a buffer that fits the L2, `repeats` passes; each pass a block reads a different slice, so the
+// lines it wants were last touched by another SM and come from the L2, not from its own L1.  Same load instruction
+// (LDG.E.128.CONSTANT) as the traversal kernels.
+__global__ void k_read(const float4 *__restrict__ a, size_t n, int repeats, float *__restrict__ sink) {
+    float acc = 0.f;
+    const size_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    for (int r = 0; r < repeats; ++r) {
+        const size_t blk = ((size_t)blockIdx.x + (size_t)r * 37u) % gridDim.x;
+        const size_t lo = blk * per_block, hi = lo + per_block < n ? lo + per_block : n;
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const float4 v = __ldg(a + i);
+            acc += (v.x + v.y) + (v.z + v.w);
+        }
+    }
+    if (acc == 123.456f) sink[0] = acc;  // keeps the loads alive
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 struct DevBuf {
     void *p = nullptr;
@@ -1917,6 +1934,29 @@ int b2pt_measure_copy_gbs(b2pt_ctx *ctx, size_t bytes, int iters, double *gbs) {
     }
     *gbs = best;
     return s.finish("measure_copy_gbs");
+}
+
+int b2pt_measure_l2_read_gbs(b2pt_ctx *ctx, size_t bytes, int repeats, int iters, double *gbs) {
+    NEED_CTX()
+    if (!gbs || iters <= 0 || repeats <= 0 || bytes < 1024) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    bytes = bytes / 16 * 16;
+    Scratch s(ctx);
+    float4 *a = (float4 *)s.dev(bytes);
+    float *sink = (float *)s.dev(16);
+    if (s.err) return s.finish("measure_l2_read_gbs");
+    CU(cudaMemsetAsync(a, 0, bytes, ctx->stream));
+    double best = 0;
+    for (int it = 0; it < iters + 1; ++it) {
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_read<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, bytes / 16, repeats, sink);
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        if (it > 0 && ms > 0) best = std::max(best, (double)repeats * (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    *gbs = best;
+    return s.finish("measure_l2_read_gbs");
 }
 
 }  // extern "C"

@@ -255,6 +255,11 @@ int b2pt_stream_uniforms(b2pt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t 
  * used by bench.py only as a cross-check of MEASURED_PEAKS.json. */
 int b2pt_measure_copy_gbs(b2pt_ctx *ctx, size_t bytes, int iters, double *gbs);
 
+/* Read throughput in GB/s of `repeats` passes over a buffer of `bytes` that fits the L2 (each pass a block reads a slice
+ * another SM read before, so the lines come from the L2): the bandwidth that bounds a traversal whose tree and
+ * primitives are cache-resident (SURVEY 8d asks for this denominator next to the HBM one).  bench.py only. */
+int b2pt_measure_l2_read_gbs(b2pt_ctx *ctx, size_t bytes, int repeats, int iters, double *gbs);
+
 #ifdef __cplusplus
 }
 #endif
