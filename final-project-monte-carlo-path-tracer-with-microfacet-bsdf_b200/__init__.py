@@ -214,6 +214,7 @@ def gpu_lib():
         L.b2pt_stream_uniforms.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32,
                                            c_float_p]
         L.b2pt_measure_copy_gbs.argtypes = [C.c_void_p, C.c_size_t, C.c_int, c_double_p]
+        L.b2pt_tonemap_rgba8.argtypes = [C.c_void_p, c_float_p, C.c_int, C.POINTER(C.c_ubyte)]
         L.b2pt_measure_l2_read_gbs.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, c_double_p]
         _gpu = L
     return _gpu
@@ -561,6 +562,16 @@ class Context:
         g = C.c_double()
         self._ck(self.L.b2pt_measure_copy_gbs(self.h, nbytes, iters, C.byref(g)))
         return g.value
+
+    def tonemap_rgba8(self, rgb=None, n_pixels=0):
+        """Renderer.cpp:93-102 on the device: RGBA8 bytes of `rgb` ([n][3] fp32), or with rgb=None of the frame the last
+        render() left on the device.  Byte-identical to the host loop (b2pt_host_tonemap_rgba8)."""
+        if rgb is not None:
+            rgb = np.ascontiguousarray(rgb, np.float32).reshape(-1, 3)
+            n_pixels = len(rgb)
+        out = np.zeros((n_pixels, 4), np.uint8)
+        self._ck(self.L.b2pt_tonemap_rgba8(self.h, fp(rgb) if rgb is not None else None, n_pixels, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return out
 
     def measure_l2_read_gbs(self, nbytes=32 << 20, repeats=64, iters=5):
         """Read bandwidth out of the L2 (GB/s): the denominator for traversal kernels whose tree is cache-resident."""

@@ -1015,6 +1015,38 @@ __global__ void k_copy(const float4 *__restrict__ a, float4 *__restrict__ b, siz
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
 
+// ---- tone map: Renderer.cpp:96-102 ------------------------------------------------------------------------------------------
+// raw = (unsigned char)clamp(0, 255, 255 * pow(c, 0.45)): the reference's object code calls the C double pow, the product
+// is narrowed to float by clamp's `const float &`, clamp(lo,hi,v) = max(lo, min(hi, v)) sends NaN to 255, the conversion
+// truncates.  The device's double pow may differ from the host's by a few ulp, which can only change a byte when the
+// product lies within rounding distance of an integer: those values (a few per frame) are listed for the host to redo.
+__device__ __forceinline__ unsigned char tonemap_byte(float x, bool *ambiguous) {
+    const double y = 255.0 * pow((double)x, (double)0.45f);  // `float inv_gamma = 0.45;`
+    const float v = (float)y;
+    const float m = (v < 255.f) ? v : 255.f;
+    const float r = (0.f < m) ? m : 0.f;
+    const double k = rint(y);
+    *ambiguous = (y > 0.5 && y < 255.5 && fabs(y - k) < 1e-4);
+    return (unsigned char)r;
+}
+__global__ void tonemap_kernel(const float *__restrict__ rgb, int n_pixels, uchar4 *__restrict__ out, unsigned *__restrict__ n_amb,
+                               uint2 *__restrict__ amb, unsigned amb_cap) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
+        unsigned char b[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float x = rgb[3 * (size_t)i + c];
+            bool a;
+            b[c] = tonemap_byte(x, &a);
+            if (a) {
+                const unsigned q = atomicAdd(n_amb, 1u);
+                if (q < amb_cap) amb[q] = make_uint2((unsigned)(3 * i + c), __float_as_uint(x));
+            }
+        }
+        out[i] = make_uchar4(b[0], b[1], b[2], 255);
+    }
+}
+
 // Read-only streaming over a buffer that fits the L2, `repeats` passes; each pass a block reads a different slice, so the
 // lines it wants were last touched by another SM and come from the L2, not from its own L1.  Same load instruction
 // (LDG.E.128.CONSTANT) as the traversal kernels.
@@ -1934,6 +1966,59 @@ int b2pt_measure_copy_gbs(b2pt_ctx *ctx, size_t bytes, int iters, double *gbs) {
     }
     *gbs = best;
     return s.finish("measure_copy_gbs");
+}
+
+int b2pt_tonemap_rgba8(b2pt_ctx *ctx, const float *rgb_host, int n_pixels, unsigned char *rgba_host) {
+    NEED_CTX()
+    if (n_pixels <= 0 || !rgba_host) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    const size_t bytes = (size_t)n_pixels * 12;
+    const float *d_rgb = nullptr;
+    Scratch s(ctx);
+    if (rgb_host) {
+        float *d = (float *)s.dev(bytes);
+        if (s.err) return s.finish("tonemap_rgba8");
+        CU(cudaMemcpyAsync(d, rgb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_rgb = d;
+    } else {  // the frame the last b2pt_render / b2pt_group_render left on this device
+        if (!ctx->fb.p || ctx->fb.bytes < bytes) return fail(ctx, B2PT_ERR_INVALID, "no device-resident frame of that size");
+        d_rgb = (const float *)ctx->fb.p;
+    }
+    const unsigned cap = 1u << 16;
+    uchar4 *d_out = (uchar4 *)s.dev((size_t)n_pixels * 4);
+    uint2 *d_amb = (uint2 *)s.dev((size_t)cap * 8);
+    unsigned *d_n = (unsigned *)s.dev(16);
+    if (s.err) return s.finish("tonemap_rgba8");
+    CU(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
+    tonemap_kernel<<<grid_for((size_t)n_pixels, ctx, 8), 256, 0, ctx->stream>>>(d_rgb, n_pixels, d_out, d_n, d_amb, cap);
+    unsigned n_amb = 0;
+    CU(cudaMemcpyAsync(rgba_host, d_out, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&n_amb, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    auto host_byte = [](float x) {
+        const float v = (float)(255 * ::pow((double)x, (double)0.45f));
+        const float m = (v < 255.f) ? v : 255.f;
+        const float r = (0.f < m) ? m : 0.f;
+        return (unsigned char)r;
+    };
+    if (n_amb > cap) {  // pathological frame (e.g. a constant sitting on a boundary): redo everything on the host
+        std::vector<float> all((size_t)n_pixels * 3);
+        const float *src = rgb_host;
+        if (!src) {
+            CU(cudaMemcpy(all.data(), d_rgb, bytes, cudaMemcpyDeviceToHost));
+            src = all.data();
+        }
+        for (size_t i = 0; i < (size_t)n_pixels; ++i)
+            for (int c = 0; c < 3; ++c) rgba_host[4 * i + c] = host_byte(src[3 * i + c]);
+    } else if (n_amb) {
+        std::vector<uint2> amb(n_amb);
+        CU(cudaMemcpy(amb.data(), d_amb, (size_t)n_amb * 8, cudaMemcpyDeviceToHost));
+        for (const uint2 &e : amb) {
+            float x;
+            std::memcpy(&x, &e.y, 4);
+            rgba_host[4 * (size_t)(e.x / 3) + e.x % 3] = host_byte(x);
+        }
+    }
+    return s.finish("tonemap_rgba8");
 }
 
 int b2pt_measure_l2_read_gbs(b2pt_ctx *ctx, size_t bytes, int repeats, int iters, double *gbs) {

@@ -251,6 +251,13 @@ int b2pt_camera_rays_batch(b2pt_ctx *ctx, const b2pt_camera *cam, const int32_t 
 int b2pt_stream_uniforms(b2pt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t tag,
                          uint32_t dim_begin, int32_t count, float *out);
 
+/* Replaces: the tone-map loop of Renderer::Render, src/Renderer.cpp:93-102 (gamma 0.45 through the C double pow,
+ * clamp with NaN -> 255, truncation to unsigned char, alpha 255).  rgb_host == NULL tone-maps the frame the last
+ * b2pt_render / b2pt_group_render left on this context's device (no upload; 4 instead of 12 bytes per pixel come
+ * back).  Bytes are identical to the host loop's: values whose product lies within rounding distance of an integer
+ * are recomputed on the host with the C library's pow. */
+int b2pt_tonemap_rgba8(b2pt_ctx *ctx, const float *rgb_host, int n_pixels, unsigned char *rgba_host);
+
 /* Device-side copy throughput of this GPU in GB/s (read+write bytes of a plain copy kernel),
  * used by bench.py only as a cross-check of MEASURED_PEAKS.json. */
 int b2pt_measure_copy_gbs(b2pt_ctx *ctx, size_t bytes, int iters, double *gbs);

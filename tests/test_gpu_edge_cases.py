@@ -101,3 +101,31 @@ def test_argument_errors(ctx):
     d.nodes[0].a = saved
     ctx.upload(sc)
     sc.close()
+
+
+def test_device_tonemap_is_byte_identical_to_the_host_loop(ctx):
+    """b2pt_tonemap_rgba8 (Renderer.cpp:93-102 on the device) against the host restatement: every byte equal, on the values
+    that sit on the truncation boundaries 255 * x^0.45 = k (and a few ulp either side), NaN / inf / negative / zero /
+    denormal inputs, random radiances, and on a rendered frame left resident on the device."""
+    rng = np.random.RandomState(5)
+    k = np.arange(0, 257, dtype=np.float64)
+    edge = ((k / 255.0) ** (1.0 / np.float64(np.float32(0.45)))).astype(np.float32)
+    around = np.concatenate([np.nextafter(edge, np.float32(np.inf)), np.nextafter(edge, np.float32(-np.inf)), edge,
+                             edge * np.float32(1 + 3e-7), edge * np.float32(1 - 3e-7)])
+    special = np.array([np.nan, np.inf, -np.inf, -1.0, -0.0, 0.0, 1e-45, 1e-38, 1.0, 1.0000001, 0.99999994, 5.0, 15.0, 20.0, 3e38], np.float32)
+    vals = np.concatenate([around, special, rng.rand(300000).astype(np.float32), (rng.rand(100000) ** 8 * 20).astype(np.float32)])
+    vals = np.resize(vals, (len(vals) + 2) // 3 * 3).reshape(-1, 3)
+    got = ctx.tonemap_rgba8(vals)
+    want = b2pt.tonemap_rgba8(vals)
+    assert np.array_equal(got, want), f"{(got != want).sum()} bytes differ"
+    assert (want[:, 3] == 255).all() and len(np.unique(want[:, :3])) == 256
+    # the frame the last render left on the device
+    sc, _ = scenes.cornell(64, 48)
+    ctx.upload(sc)
+    fb, _ = ctx.render(sc.camera, 4)
+    got = ctx.tonemap_rgba8(None, 64 * 48)
+    assert np.array_equal(got, b2pt.tonemap_rgba8(fb.reshape(-1, 3)))
+    # a constant frame sitting exactly on a boundary: more ambiguous values than the list holds -> host fallback, still identical
+    const = np.full((70000, 3), edge[100], np.float32)
+    assert np.array_equal(ctx.tonemap_rgba8(const), b2pt.tonemap_rgba8(const))
+    sc.close()
