@@ -17,6 +17,10 @@
 //   --chunk N              samples per pixel per b2pt_render call (progress granularity; default 256: the thin tail of deep paths at the end of a call costs ~2 ms)
 //   --gpus N               split the samples over N GPUs of this box (one NCCL reduce of the frame per call)
 //   --host-tonemap         tone map on the host like the reference (default: on the device, byte-identical)
+//   --checkpoint FILE      after every chunk, save the fp32 accumulation + the samples done (the reference has no checkpoints:
+//                          a 2048-spp run that dies after two hours starts over); --resume FILE continues such a run with the
+//                          same sample streams, --stop-after N ends after N samples per pixel (still writes the PNG)
+//   --preview-every N      also rewrite the PNG from the partial frame every N chunks (scaled by spp / samples done)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -50,6 +54,8 @@ int main(int argc, char **argv) {
     std::string conf = "conf.json", run_dir = ".";
     int spp = 0, width = 0, height = 0, device = 0, fix = 0, ndir = 0, chunk = 256, gpus = 1;
     bool host_tonemap = false;
+    std::string checkpoint, resume;
+    int stop_after = 0, preview_every = 0;
     unsigned long long seed = 0x5EED0001ull;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -64,6 +70,10 @@ int main(int argc, char **argv) {
         else if (a == "--seed") seed = std::strtoull(next(), nullptr, 0);
         else if (a == "--chunk") chunk = std::max(1, std::atoi(next()));
         else if (a == "--host-tonemap") host_tonemap = true;
+        else if (a == "--checkpoint") checkpoint = next();
+        else if (a == "--resume") resume = next();
+        else if (a == "--stop-after") stop_after = std::max(0, std::atoi(next()));
+        else if (a == "--preview-every") preview_every = std::max(0, std::atoi(next()));
         else if (a == "--gpus") gpus = std::max(1, std::atoi(next()));
         else if (a == "--fix-ndir") fix |= B2PT_HOST_FIX_DIRECT_LIGHT_SAMPLE;
         else if (a == "--fix-quality") fix |= B2PT_HOST_FIX_MODEL_QUALITY;
@@ -105,9 +115,52 @@ int main(int argc, char **argv) {
     std::cout << "SPP: " << total_spp << "\n";
     unsigned long long rays = 0;
     double gpu_ms = 0;
-    for (int s0 = 0; s0 < total_spp; s0 += chunk) {
+    // checkpoint file: magic, width, height, spp_total, samples done, seed, then the fp32 accumulation (sum_k rgb_k / spp_total)
+    struct CkptHeader { char magic[8]; int32_t width, height, spp_total, done; uint64_t seed; };
+    int first_sample = 0;
+    if (!resume.empty()) {
+        FILE *f = std::fopen(resume.c_str(), "rb");
+        CkptHeader h{};
+        if (!f || std::fread(&h, sizeof h, 1, f) != 1 || std::memcmp(h.magic, "B2PTCKP1", 8) != 0 || h.width != cam->width || h.height != cam->height ||
+            h.spp_total != total_spp || h.seed != seed || h.done < 0 || h.done > total_spp ||
+            std::fread(framebuffer.data(), sizeof(float), framebuffer.size(), f) != framebuffer.size()) {
+            std::fprintf(stderr, "cannot resume from %s: missing, truncated, or written for another frame size / spp / seed\n", resume.c_str());
+            return 1;
+        }
+        std::fclose(f);
+        first_sample = h.done;
+    }
+    auto save_checkpoint = [&](int done) {
+        if (checkpoint.empty()) return true;
+        const std::string tmp = checkpoint + ".tmp";
+        FILE *f = std::fopen(tmp.c_str(), "wb");
+        CkptHeader h{{'B', '2', 'P', 'T', 'C', 'K', 'P', '1'}, cam->width, cam->height, total_spp, done, seed};
+        bool ok = f && std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(framebuffer.data(), sizeof(float), framebuffer.size(), f) == framebuffer.size();
+        if (f) ok = (std::fclose(f) == 0) && ok;
+        ok = ok && std::rename(tmp.c_str(), checkpoint.c_str()) == 0;  // a crash never leaves a half-written checkpoint behind
+        if (!ok) std::fprintf(stderr, "\ncannot write checkpoint %s\n", checkpoint.c_str());
+        return ok;
+    };
+    std::vector<unsigned char> raw((size_t)4 * cam->width * cam->height);
+    auto write_image = [&](int done) {  // Renderer.cpp:93-109 on the frame accumulated so far
+        if (done == total_spp && !host_tonemap && first_sample == 0 && b2pt_tonemap_rgba8(ctx, nullptr, cam->width * cam->height, raw.data()) == B2PT_OK) {
+            // the whole frame is still resident on the device: 4 instead of 12 bytes per pixel come back, and the host is
+            // spared 6 M double pow calls; byte-identical to the host loop
+        } else if (done == total_spp) {
+            b2pt_host_tonemap_rgba8(framebuffer.data(), cam->width * cam->height, raw.data());
+        } else {  // partial frame: the accumulation is divided by spp_total, show it divided by the samples done
+            std::vector<float> scaled(framebuffer.size());
+            const float k = (float)total_spp / (float)std::max(done, 1);
+            for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = framebuffer[i] * k;
+            b2pt_host_tonemap_rgba8(scaled.data(), cam->width * cam->height, raw.data());
+        }
+        return b2pt_host_write_png_rgba8(path.c_str(), raw.data(), cam->width, cam->height) == 0;
+    };
+    const int last_sample = stop_after > 0 ? std::min(total_spp, stop_after) : total_spp;
+    int done = first_sample, chunks = 0;
+    for (int s0 = first_sample; s0 < last_sample; s0 += chunk) {
         b2pt_render_params p{};
-        p.spp_total = total_spp; p.sample_begin = s0; p.sample_count = std::min(chunk, total_spp - s0);
+        p.spp_total = total_spp; p.sample_begin = s0; p.sample_count = std::min(chunk, last_sample - s0);
         p.seed = seed;
         // short jobs: a 16 Mi ray queue (27 GB) instead of the library's 48 Mi (82 GB) — allocating and releasing the larger one
         // costs more wall time than its 4 % buys unless the render runs for several seconds
@@ -117,21 +170,16 @@ int main(int argc, char **argv) {
         if (b2pt_group_render(ctxs.data(), gpus, cam, &p, framebuffer.data(), &st) != B2PT_OK) { std::fprintf(stderr, "\nb2pt_render: %s\n", b2pt_last_error(ctx)); return 1; }
         rays += st.rays_reference;
         gpu_ms += st.gpu_ms;
-        update_progress((float)(s0 + p.sample_count) / (float)total_spp);
+        done = s0 + p.sample_count;
+        ++chunks;
+        if (!save_checkpoint(done)) return 1;
+        if (preview_every > 0 && chunks % preview_every == 0 && done < last_sample) write_image(done);
+        update_progress((float)done / (float)total_spp);
     }
     update_progress(1.f);
     std::cout << std::endl;
     std::cout << "Writing image to " << path << std::endl;
-    std::vector<unsigned char> raw((size_t)4 * cam->width * cam->height);
-    // tone map on the device (the frame is still resident there: 4 instead of 12 bytes per pixel come back, and the host is
-    // spared 6 M double pow calls); byte-identical to the host loop, which --host-tonemap selects
-    if (host_tonemap) b2pt_host_tonemap_rgba8(framebuffer.data(), cam->width * cam->height, raw.data());
-    else if (b2pt_tonemap_rgba8(ctx, nullptr, cam->width * cam->height, raw.data()) != B2PT_OK) {
-        std::fprintf(stderr, "b2pt_tonemap_rgba8: %s\n", b2pt_last_error(ctx));
-        return 1;
-    }
-    if (b2pt_host_write_png_rgba8(path.c_str(), raw.data(), cam->width, cam->height) != 0)
-        std::cerr << "Error when writing image : " << b2pt_host_last_error() << std::endl;
+    if (!write_image(done)) std::cerr << "Error when writing image : " << b2pt_host_last_error() << std::endl;
     auto stop = std::chrono::system_clock::now();
 
     using Milli = std::chrono::milliseconds;

@@ -61,6 +61,31 @@ def test_demo_and_overrides(tmp_path):
         ref.close(); sc.close()
 
 
+def test_checkpoint_resume_and_preview(tmp_path):
+    """A run stopped after half of its samples and resumed from its checkpoint ends with the image of the uninterrupted run
+    (same sample streams: the frame does not depend on how the samples are split over calls or processes)."""
+    build = tmp_path / "build"
+    build.mkdir()
+    common = [EXE, "--demo", "--spp", "8", "--width", "64", "--height", "48", "--chunk", "2"]
+    r = run(common, str(build))
+    assert r.returncode == 0, r.stderr
+    whole = b2pt.read_png(str(build / "output.png")).astype(int)
+    ck = str(build / "half.ckpt")
+    r = run(common + ["--checkpoint", ck, "--stop-after", "4", "--preview-every", "1"], str(build))
+    assert r.returncode == 0, r.stderr
+    half = b2pt.read_png(str(build / "output.png")).astype(int)
+    assert os.path.getsize(ck) == 32 + 64 * 48 * 3 * 4
+    # the 4-of-8-spp preview is scaled by spp / samples done: about as bright as the whole frame, only noisier
+    assert abs(half[..., :3].mean() - whole[..., :3].mean()) < 0.08 * whole[..., :3].mean()
+    r = run(common + ["--resume", ck], str(build))
+    assert r.returncode == 0, r.stderr
+    resumed = b2pt.read_png(str(build / "output.png")).astype(int)
+    assert (np.abs(resumed - whole) <= 1).mean() > 0.999  # atomics order: last-bit differences at most
+    # a checkpoint written for another spp is refused
+    r = run([EXE, "--demo", "--spp", "16", "--width", "64", "--height", "48", "--resume", ck], str(build))
+    assert r.returncode != 0 and "cannot resume" in r.stderr
+
+
 def test_bad_arguments_fail_loudly(tmp_path):
     build = tmp_path / "build"
     build.mkdir()
