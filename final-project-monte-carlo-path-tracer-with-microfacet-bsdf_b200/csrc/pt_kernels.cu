@@ -450,9 +450,11 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
 // EPSILON of dist" half of the visibility test from the light neighbourhood table (no traversal).  A sample whose window
 // holds no hit is rejected here and never becomes a shadow ray; the others are compacted into the shadow queue for the
 // occluder search.
-__global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *__restrict__ vtx_pn, const uint2 *__restrict__ vtx_ps,
-                                                     const unsigned *__restrict__ n_ptr, unsigned char *__restrict__ vis,
-                                                     float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt, uint32_t k0, uint32_t k1) {
+__global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const float4 *__restrict__ vtx_pn, const uint2 *__restrict__ vtx_ps,
+                                                     const uint32_t *__restrict__ vtx_ray, const int *__restrict__ hit_prim,
+                                                     const float *__restrict__ hit_t, const unsigned *__restrict__ n_ptr,
+                                                     unsigned char *__restrict__ vis, float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt,
+                                                     uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
     const unsigned ndir = (unsigned)S.n_dir;
@@ -471,15 +473,41 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *
             Stream rs = stream_open(k0, k1, ps.x, ps.y, STREAM_PATH, __float_as_uint(a.w) + 4u * k);
             float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
             g = nee_geometry(S, pn, u0, u1, u2, u3);
-            w = window_witness(S, make_ray(pn, g.ws), g.dist, g.lnode);
-            if (w == 0) vis[i] = 0;
-            else queue = true;
+            // A sample whose summand Le * f * cos * cos' / d^2 / pdf / N is zero whatever its visibility (Material::eval returns
+            // its literal 0: light on the wrong side of the surface for the lobe, or outside the 0.8 degree cone of a smooth
+            // material — i.e. nearly every sample taken on the mirror floor, the gold king and the glass pieces) needs no
+            // visibility test at all: adding +-0 leaves l_dir unchanged (Scene.cpp:76-79).  The reference traces those shadow
+            // rays; they are still counted as rays it needs (light_kernel), just never traced here.
+            bool dead;
+            {
+                const unsigned ri = vtx_ray[v];
+                const float4 o4 = q.o[ri], d4 = q.d[ri];
+                const uint32_t mask = (q.info[ri] >> INFO_MASK_SHIFT) & 7u;
+                Ray r;
+                r.o = xyz(o4); r.d = xyz(d4);
+                f3 hp, hn;
+                uint32_t mat, kind;
+                hit_point(S, r, hit_prim[ri], hit_t[ri], &hp, &hn, &mat, &kind);
+                const Material &m = S.mats[mat];
+                const f3 wo = -r.d;
+                const bool inner = dot(wo, hn) < 0;
+                dead = true;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if ((mask >> c & 1u) && !nee_term_is_zero(m, g, wo, hn, c, !inner)) dead = false;
+            }
+            if (dead) vis[i] = 0;
+            else {
+                w = window_witness(S, make_ray(pn, g.ws), g.dist, g.lnode);
+                if (w == 0) vis[i] = 0;
+                else queue = true;
+            }
         }
-        const unsigned q = block_alloc(queue ? 1u : 0u, &cnt->n_shadow);
+        const unsigned qx = block_alloc(queue ? 1u : 0u, &cnt->n_shadow);
         if (queue) {
-            sh_o[q] = make_float4(pn.x, pn.y, pn.z, g.dist);
+            sh_o[qx] = make_float4(pn.x, pn.y, pn.z, g.dist);
             // w == 1: a witness exists, only occluders are searched (phase 2); w < 0: no table entry, search the window first
-            sh_d[q] = make_float4(g.ws.x, g.ws.y, g.ws.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
+            sh_d[qx] = make_float4(g.ws.x, g.ws.y, g.ws.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
         }
     }
 }
@@ -1280,8 +1308,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             terminal_kernel<<<grid_for(n, ctx, 16), kBlock, 0, ctx->side[0]>>>(S, qa, ctx->wb.lists, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
         }
         if (S.enable_shadow) {
-            nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, ctx->wb.vtx_ps, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o,
-                                                                                ctx->wb.sh_d, dc, gp.k0, gp.k1);
+            nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, qa, ctx->wb.vtx_pn, ctx->wb.vtx_ps, ctx->wb.vtx_ray, ctx->wb.hit_prim,
+                                                                                ctx->wb.hit_t, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o, ctx->wb.sh_d, dc, gp.k0, gp.k1);
             launches++;
             CU(cudaEventRecord(ctx->tev[ring][2], st));
             if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);

@@ -876,6 +876,29 @@ PT_HD_NI float mat_pdf(const Material &m, f3 wi, f3 wo, f3 N, int c, bool is_ref
     return (fabsf(dot(h, N)) > 1 - kEps) ? 1.0f : 0.0f;
 }
 
+// True when Material::eval returns its literal 0 for these directions: the light is on the wrong side for the lobe, the
+// lobe does not exist for the material, or (smooth types) the half vector is outside the 1 - EPSILON cone around N
+// (src/Material.hpp:334-336,357-359,379-381,395-397).  The same comparisons as in mat_eval below, which stays the one place
+// that computes values; used to drop next-event samples whose summand is zero whatever their visibility.
+PT_HD bool mat_eval_returns_zero(const Material &m, f3 wi, f3 wo, f3 N, int c, bool is_reflect) {
+    const float sides = dot(wi, N) * dot(wo, N);
+    if (mat_is_rough(m)) {
+        if (is_reflect) return sides <= 0;
+        return m.type == MAT_ROUGH_CONDUCTOR || sides >= 0;
+    }
+    if (is_reflect) {
+        f3 h = normalized(wi + wo);
+        h = (dot(wi, N) > 0) ? h : -h;
+        return sides <= 0 || dot(h, N) < 1 - kEps;
+    }
+    if (m.type == MAT_SMOOTH_CONDUCTOR || sides >= 0) return true;
+    float ior = mat_ior(m, c);
+    float eta = (dot(wi, N) > 0) ? ior : (float)(1. / (double)ior);
+    f3 h = normalized((-wi) - wo * eta);
+    h = (dot(h, N) > 0) ? h : -h;
+    return dot(h, N) < 1 - kEps;
+}
+
 PT_HD_NI float mat_eval(const Material &m, f3 wi, f3 wo, f3 N, int c, float u, float v, bool is_reflect) {  // eval, :330-408
     if (mat_is_rough(m)) {
         if (is_reflect) {
@@ -1048,6 +1071,17 @@ PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u
     g.dist = norm(d);
     g.n_light = ls.n; g.emit = ls.emit; g.pdf = ls.pdf; g.lnode = ls.node;
     return g;
+}
+// The summand of Scene::directLighting is Le * f * cos * cos' / d^2 / pdf / N (below).  When f is the literal 0 and every other
+// factor is finite with non-zero denominators the summand is +-0, and adding it leaves l_dir as it is: such a sample needs
+// neither its visibility test nor its evaluation.  (A non-finite factor would make 0 * x a NaN: those samples are kept.)
+PT_HD bool nee_term_is_zero(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, bool is_reflect) {
+    const float rest = dot(g.ws, n) * dot(-g.ws, g.n_light);
+    const float e = comp(g.emit, c);
+    if (!(fabsf(rest) < INFINITY) || !(fabsf(e) < INFINITY) || !(g.dist > 0.f) || !(g.dist < INFINITY) || !(g.dist * g.dist > 0.f) || !(g.pdf > 0.f) ||
+        !(g.pdf < INFINITY))
+        return false;
+    return mat_eval_returns_zero(m, g.ws, wo, n, c, is_reflect);
 }
 PT_HD float nee_term(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, float u, float v, bool is_reflect, int n_dir) {
     float emit = comp(g.emit, c);

@@ -193,6 +193,10 @@ void hc_eval(void *h, int mat, const float *wi, const float *wo, const float *N,
     const Material &m = ((HcScene *)h)->view.mats[mat];
     for (long i = 0; i < n; ++i) out[i] = mat_eval(m, V(wi + 3 * i), V(wo + 3 * i), V(N + 3 * i), wl[i], uv[2 * i], uv[2 * i + 1], refl[i] != 0);
 }
+void hc_eval_returns_zero(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *refl, long n, int *out) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    for (long i = 0; i < n; ++i) out[i] = mat_eval_returns_zero(m, V(wi + 3 * i), V(wo + 3 * i), V(N + 3 * i), wl[i], refl[i] != 0) ? 1 : 0;
+}
 void hc_pdf(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *refl, long n, float *out) {
     const Material &m = ((HcScene *)h)->view.mats[mat];
     for (long i = 0; i < n; ++i) out[i] = mat_pdf(m, V(wi + 3 * i), V(wo + 3 * i), V(N + 3 * i), wl[i], refl[i] != 0);

@@ -342,6 +342,13 @@ class HostCheck:
         self.L.hc_eval(self.h, mat, fp(wi), fp(wo), fp(n), ip(wl), fp(uv), ip(rf), C.c_long(len(wl)), fp(out))
         return out
 
+    def bsdf_eval_returns_zero(self, mat, wi, wo, n, wl, rf):
+        """pt::mat_eval_returns_zero: the predicate the nee kernel uses to drop light samples whose summand is zero."""
+        wi, wo, n, wl, rf = f32(wi), f32(wo), f32(n), i32(wl), i32(rf)
+        out = np.zeros(len(wl), np.int32)
+        self.L.hc_eval_returns_zero(self.h, mat, fp(wi), fp(wo), fp(n), ip(wl), ip(rf), C.c_long(len(wl)), ip(out))
+        return out
+
     def bsdf_pdf(self, mat, wi, wo, n, wl, rf):
         wi, wo, n, wl, rf = f32(wi), f32(wo), f32(n), i32(wl), i32(rf)
         out = np.zeros(len(wl), np.float32)

@@ -148,6 +148,25 @@ def test_bsdf_parity():
     hc.close(); ref.close(); sc.close()
 
 
+def test_zero_summand_predicate_implies_eval_zero():
+    """mat_eval_returns_zero (used to drop light samples before any visibility work) is true ONLY where the reference's own
+    Material::eval returns its literal 0 — for every material, lobe and wavelength, including directions on the smooth cones'
+    edges — and it catches the bulk of them for the smooth materials (otherwise it would not be worth having)."""
+    sc, _ = scenes.two_triangle_scene()
+    ref, hc = S.Ref(sc), S.HostCheck(sc)
+    rng = np.random.RandomState(12)
+    wi, wo, nrm, wl, uv, rf = bsdf_inputs(rng, 40000)
+    for mat, name in enumerate(b2pt.NAMED_MATERIALS):
+        gate = hc.bsdf_eval_returns_zero(mat, wi, wo, nrm, wl, rf) != 0
+        f_ref = ref.bsdf_eval(mat, wi, wo, nrm, wl, uv, rf)
+        f_hc = hc.bsdf_eval(mat, wi, wo, nrm, wl, uv, rf)
+        assert (f_ref[gate] == 0).all() and (f_hc[gate] == 0).all(), name
+        assert gate.mean() > 0.3, (name, gate.mean())
+        if "smooth" in name or name in ("gold_conductor", "silver_mirror"):
+            assert (gate | (f_ref != 0)).mean() > 0.999, name  # nearly every zero of a smooth material is one the predicate names
+    ref.close(); hc.close(); sc.close()
+
+
 def test_textured_reflectance():
     """Checkerboard reflectance (Material.hpp:134-151) through eval on a textured smooth conductor."""
     sc, _ = scenes.two_triangle_scene()
