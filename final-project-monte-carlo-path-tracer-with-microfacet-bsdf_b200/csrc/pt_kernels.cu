@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
     unsigned long long refs = 0;
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
         unsigned i = it + threadIdx.x;
-        bool want = false;
+        bool want = false, shaded = false;
         int cls = -1;
         unsigned vb = 0;
         Ray r;
@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                     Stream rr_s = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), STREAM_PATH, dim_rr);
                     const bool survives = stream_next(rr_s) < S.rr_rate;
                     cls = 1 + 2 * m.type + (survives ? 1 : 0);
-                    want = true;  // light samples are evaluated whether or not shadow rays are traced (Scene.cpp:74)
+                    shaded = true;
+                    // light samples are evaluated whether or not shadow rays are traced (Scene.cpp:74) — unless no point of the
+                    // lights can contribute to this vertex at all (pt::nee_vertex_is_dead): then it gets no record and no slots
+                    want = !nee_vertex_is_dead(S, m, -r.d, nn, p + nn * kEps);
                 }
             }
         }
@@ -438,8 +441,9 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
             vtx_pn[v] = make_float4(pn.x, pn.y, pn.z, __uint_as_float(dim));
             vtx_ps[v] = make_uint2(__float_as_uint(o4.w), __float_as_uint(d4.w));
             vtx_ray[v] = i;
-            refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
         }
+        // rays the reference needs: ndir shadow rays per shaded vertex and wavelength path, traced here or not
+        if (shaded) refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
     }
     refs = warp_sum(refs);
     if (lane == 0 && refs) atomicAdd(&cnt->rays_reference, refs);
@@ -805,7 +809,7 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
             const uint32_t sb = sh_base[i];
             // the accepted samples' terms (nee_eval_kernel) are added in sample order, the order l_dir accumulates in (Scene.cpp:76-79)
             for (int k = 0; k < ndir; ++k) {
-                if (S.enable_shadow && !(sb != kNoShadow && vis[sb + k])) continue;
+                if (sb == kNoShadow || (S.enable_shadow && !vis[sb + k])) continue;  // kNoShadow: no light point can contribute here
                 const float *tv = nee_val + 3 * (size_t)(sb + k);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
@@ -1563,6 +1567,8 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;
+    for (int k = 0; k < 3; ++k) v.light_c[k] = packed.light_sphere[k];
+    v.light_r = packed.light_sphere[3];
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height;
     v.env = nullptr;
     v.env_tex = 0;

@@ -216,6 +216,7 @@ struct SceneView {
     const int *ln_left, *ln_right, *ln_prim;
     const float4 *lt_entries;  // light neighbourhood table (pt_pack.hpp): 2 float4 per entry
     const int *lt_off, *lt_cnt;
+    float light_c[3], light_r;  // a sphere around every point a light sample can fall on (pt_pack.hpp); light_r < 0: unknown
     int use_env, env_w, env_h;
     const float4 *env;      // texels as float4 (rgb, 0)
     unsigned long long env_tex;  // the same texels as a point-sampled CUDA texture object (device only; 0 = use `env`)
@@ -1082,6 +1083,36 @@ PT_HD bool nee_term_is_zero(const Material &m, const NeeGeom &g, f3 wo, f3 n, in
         !(g.pdf < INFINITY))
         return false;
     return mat_eval_returns_zero(m, g.ws, wo, n, c, is_reflect);
+}
+// The same question for a whole vertex, before any light sample is drawn: can ANY point of the lights give a non-zero
+// summand?  Conservative (never true when a sample could be alive):
+//  * a conductor seen from its back side is asked for its transmission lobe, which it does not have;
+//  * both lobes need the light on the +n side of the surface (reflect: dot(wi,n) dot(wo,n) > 0 with dot(wo,n) >= 0; transmit:
+//    < 0 with dot(wo,n) < 0), so a light sphere entirely below the tangent plane gives nothing;
+//  * the reflect lobe of a smooth material wants the half vector within acos(1 - EPSILON) = 0.81 degrees of n, i.e. wi within
+//    1.62 degrees (0.0283 rad) of the mirror direction: nothing if the light sphere stays outside a 0.03 rad cone around it.
+// pn is the point the light samples are aimed from (Scene.cpp:114).  Margins are far above float rounding.
+PT_HD bool nee_vertex_is_dead(const SceneView &S, const Material &m, f3 wo, f3 n, f3 pn) {
+    if (!(S.light_r >= 0.f)) return false;
+    const float won = dot(wo, n);
+    if (!(won == won)) return false;
+    const bool inner = won < 0;
+    if (inner && mat_is_conductor(m)) return true;
+    if (!inner && won == 0.f) return true;  // dot(wi,n) * 0 <= 0 for every wi
+    const f3 c = mk3(S.light_c[0], S.light_c[1], S.light_c[2]) - pn;
+    const float d = norm(c);
+    if (!(d < INFINITY)) return false;
+    if (dot(c, n) + S.light_r * 1.001f < -1e-3f * (d + S.light_r)) return true;
+    if (!mat_is_rough(m) && !inner && d > S.light_r * 1.001f) {
+        const f3 mdir = n * (2.f * won) - wo;
+        const float ml = norm(mdir);
+        if (!(ml > 0.5f && ml < 2.f)) return false;
+        const float cosang = dot(mdir, c) / (d * ml);
+        const float sa = S.light_r * 1.001f / d, ca = sqrtf(fmaxf(0.f, 1.f - sa * sa));
+        const float cos_lim = 0.99955003f * ca - 0.029995501f * sa;  // cos(0.03 + asin(sa))
+        if (cosang < cos_lim - 1e-4f) return true;
+    }
+    return false;
 }
 PT_HD float nee_term(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, float u, float v, bool is_reflect, int n_dir) {
     float emit = comp(g.emit, c);

@@ -19,6 +19,7 @@ struct PackedScene {
     std::vector<b2pt_node> nodes_ref;   // the reference's topology, EMPTY boxes rewritten to NaN
     std::vector<b2pt_node> nodes_fast;  // binned-SAH tree over the same leaves (pt_build.hpp)
     int fast_depth = 0;
+    float light_sphere[4] = {0.f, 0.f, 0.f, -1.f};  // centre, radius of a sphere around every light primitive (radius < 0: none)
     QuadTree quads;                     // nodes_fast collapsed four-wide; empty when its stack need exceeds kStackSize4
     // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
@@ -127,6 +128,46 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
             out.lt_cnt[ln] = cnt;
         }
         if (out.lt_entries.empty()) out.lt_entries.push_back(make_float4(0, 0, 0, 0));
+    }
+    {
+        // bounding sphere of everything a light sample can fall on: the vertices of the light triangles (Triangle::Sample returns
+        // a convex combination of them), or centre +- radius of a sphere
+        BuildBox lb = box_empty_b();
+        std::vector<float> pts;
+        for (uint32_t ln = 0; ln < d->n_light_nodes; ++ln) {
+            if (d->light_node_prim[ln] < 0) continue;
+            const uint32_t L = (uint32_t)d->light_node_prim[ln];
+            if (L >= d->n_prims) continue;
+            const float *v0 = d->prim_v0 + 4 * (size_t)L, *e1 = d->prim_e1 + 4 * (size_t)L, *e2 = d->prim_e2 + 4 * (size_t)L, *v12 = d->prim_v1v2 + 6 * (size_t)L;
+            if (d->prim_kind[L] == B2PT_NODE_SPHERE) {
+                for (int sx = -1; sx <= 1; sx += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sz = -1; sz <= 1; sz += 2) {
+                    pts.push_back(v0[0] + sx * v0[3]); pts.push_back(v0[1] + sy * v0[3]); pts.push_back(v0[2] + sz * v0[3]);
+                }
+            } else {
+                for (int k = 0; k < 3; ++k) pts.push_back(v0[k]);
+                for (int k = 0; k < 3; ++k) pts.push_back(v12[k]);
+                for (int k = 0; k < 3; ++k) pts.push_back(v12[3 + k]);
+                for (int k = 0; k < 3; ++k) pts.push_back(v0[k] + e1[k]);  // the same vertices through the edges (whichever the sampler uses)
+                for (int k = 0; k < 3; ++k) pts.push_back(v0[k] + e2[k]);
+            }
+        }
+        out.light_sphere[3] = -1.f;
+        if (!pts.empty()) {
+            for (size_t i = 0; i < pts.size(); i += 3)
+                for (int k = 0; k < 3; ++k) { lb.mn[k] = std::fmin(lb.mn[k], pts[i + k]); lb.mx[k] = std::fmax(lb.mx[k], pts[i + k]); }
+            double c[3], r2 = 0;
+            for (int k = 0; k < 3; ++k) c[k] = 0.5 * ((double)lb.mn[k] + (double)lb.mx[k]);
+            for (size_t i = 0; i < pts.size(); i += 3) {
+                double q = 0;
+                for (int k = 0; k < 3; ++k) q += (pts[i + k] - c[k]) * (pts[i + k] - c[k]);
+                r2 = std::max(r2, q);
+            }
+            const double r = std::sqrt(r2) * 1.0001 + 1e-4;
+            if (std::isfinite(r) && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2])) {
+                for (int k = 0; k < 3; ++k) out.light_sphere[k] = (float)c[k];
+                out.light_sphere[3] = (float)r;
+            }
+        }
     }
     out.mats.resize(d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {

@@ -58,6 +58,8 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
     v.tri = h->packed.tri.data();
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
+    for (int k = 0; k < 3; ++k) v.light_c[k] = h->packed.light_sphere[k];
+    v.light_r = h->packed.light_sphere[3];
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height; v.env = h->packed.env.data();
     for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
     v.rr_rate = d->rr_rate; v.inv_rr = d->inv_rr; v.enable_shadow = d->enable_shadow; v.n_dir = d->n_dir_sample;
@@ -196,6 +198,36 @@ void hc_eval(void *h, int mat, const float *wi, const float *wo, const float *N,
 void hc_eval_returns_zero(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *refl, long n, int *out) {
     const Material &m = ((HcScene *)h)->view.mats[mat];
     for (long i = 0; i < n; ++i) out[i] = mat_eval_returns_zero(m, V(wi + 3 * i), V(wo + 3 * i), V(N + 3 * i), wl[i], refl[i] != 0) ? 1 : 0;
+}
+// vertex-level and sample-level "this light sample contributes exactly zero" predicates of the nee path, for the rays of a
+// batch: per ray the first hit is the vertex; out_vertex[i] = nee_vertex_is_dead, out_alive[i] = number of the `samples` light
+// samples (uniforms u4[i][s][4]) whose summand is NOT known to be zero for wavelength 0..2 (any of them); -1 = no vertex
+void hc_nee_dead(void *h, const float *o, const float *d, const float *u4, long n, int samples, int *out_vertex, int *out_alive) {
+    const SceneView &S = ((HcScene *)h)->view;
+    for (long i = 0; i < n; ++i) {
+        out_vertex[i] = 0; out_alive[i] = -1;
+        TravStats st{0, 0};
+        Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
+        Hit hit = closest_hit4<false>(S, r, &st);
+        if (hit.prim < 0) continue;
+        Surface sf = surface_at(S, r, hit);
+        const Material &m = S.mats[sf.mat];
+        if (m.emissive) continue;
+        const f3 wo = -r.d;
+        const f3 pn = sf.p + sf.n * kEps;
+        const bool inner = dot(wo, sf.n) < 0;
+        out_vertex[i] = nee_vertex_is_dead(S, m, wo, sf.n, pn) ? 1 : 0;
+        int alive = 0;
+        for (int s = 0; s < samples; ++s) {
+            const float *u = u4 + 4 * ((size_t)i * samples + s);
+            NeeGeom g = nee_geometry(S, pn, u[0], u[1], u[2], u[3]);
+            bool dead = true;
+            for (int c = 0; c < 3; ++c)
+                if (!nee_term_is_zero(m, g, wo, sf.n, c, !inner)) dead = false;
+            if (!dead) ++alive;
+        }
+        out_alive[i] = alive;
+    }
 }
 void hc_pdf(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *refl, long n, float *out) {
     const Material &m = ((HcScene *)h)->view.mats[mat];

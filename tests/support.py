@@ -342,6 +342,16 @@ class HostCheck:
         self.L.hc_eval(self.h, mat, fp(wi), fp(wo), fp(n), ip(wl), fp(uv), ip(rf), C.c_long(len(wl)), fp(out))
         return out
 
+    def nee_dead(self, o, d, samples, rng):
+        """For the first hit of every ray: (vertex-level verdict pt::nee_vertex_is_dead, number of `samples` random light samples
+        whose summand is not known to be zero; -1 where the ray has no shaded vertex)."""
+        o, d = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
+        n = len(o)
+        u4 = (np.floor(rng.rand(n, samples, 4) * 16777216.0) / 16777216.0).astype(np.float32)
+        v, a = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.hc_nee_dead(self.h, fp(o), fp(d), fp(u4), C.c_long(n), samples, ip(v), ip(a))
+        return v, a
+
     def bsdf_eval_returns_zero(self, mat, wi, wo, n, wl, rf):
         """pt::mat_eval_returns_zero: the predicate the nee kernel uses to drop light samples whose summand is zero."""
         wi, wo, n, wl, rf = f32(wi), f32(wo), f32(n), i32(wl), i32(rf)

@@ -167,6 +167,24 @@ def test_zero_summand_predicate_implies_eval_zero():
     ref.close(); hc.close(); sc.close()
 
 
+def test_vertex_level_verdict_never_drops_a_live_light_sample(world):
+    """pt::nee_vertex_is_dead (light_kernel gives such vertices no light samples at all) is conservative: wherever it holds,
+    every one of 64 random light samples has a summand that the per-sample predicate also knows to be zero."""
+    name, sc, ref, hc = world
+    rng = np.random.RandomState(21)
+    o, d, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=3000, samples=1, seed=9)
+    # add rays that start just below the surfaces (vertices seen from the inside)
+    prim, t, co, nn, uv = ref.intersect(o[:3000], d[:3000])
+    hit = prim >= 0
+    inside_o = (co[hit] - nn[hit] * np.float32(1e-3)).astype(np.float32)
+    O, D = np.concatenate([o, inside_o]), np.concatenate([d, d[:3000][hit]])
+    v, a = hc.nee_dead(O, D, 64, rng)
+    has = a >= 0
+    assert has.sum() > 1000
+    assert not ((v == 1) & (a > 0)).any(), f"{name}: {((v == 1) & (a > 0)).sum()} vertices called dead have live samples"
+    assert (v[has] == 1).mean() > 0.1, (name, (v[has] == 1).mean())
+
+
 def test_textured_reflectance():
     """Checkerboard reflectance (Material.hpp:134-151) through eval on a textured smooth conductor."""
     sc, _ = scenes.two_triangle_scene()
