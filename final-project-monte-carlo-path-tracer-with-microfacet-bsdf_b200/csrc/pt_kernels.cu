@@ -875,6 +875,33 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
                 }
                 uint32_t nd = depth < 255u ? depth + 1u : 255u;
                 new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT);
+                // Whatever the rest of the path returns, this level returns A + clamp(0, 5, .) in [A, A + 5] (Scene.cpp:147,174,
+                // 180-183; NaN -> 5).  The map from this level's value to the pixel is monotone (affine, then clamped), so when
+                // it takes the same value at both ends of that interval — an outer clamp is saturated, typically by a brightly
+                // lit vertex further down the path — the continuation cannot change the pixel: the path ends here with that
+                // value and its ray is not emitted.
+                if (!rs.primary) {
+                    uint32_t settled = 0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (j >= rs.nch) continue;
+                        const float lo = phi_apply(rs.phi[j], lvl_A[j]), hi = phi_apply(rs.phi[j], lvl_A[j] + 5.f);
+                        if (lo == hi) {
+                            atomicAdd(acc + rs.ch[j], lo / sp.div);
+                            settled |= 1u << rs.ch[j];
+                        }
+                    }
+                    if (settled) {
+                        int kept = 0;
+                        for (int k = 0; k < n_emit; ++k) {
+                            const uint32_t mk = e_mask[k] & ~settled;
+                            if (!mk) continue;
+                            e_o[kept] = e_o[k]; e_d[kept] = e_d[k]; e_mask[kept] = mk;
+                            ++kept;
+                        }
+                        n_emit = kept;
+                    }
+                }
             }
         }
         if (!CONT) continue;
