@@ -279,6 +279,25 @@ void hc_phi_chain(const float *levels, const float *terminal, long n, int depth,
         out_phi[i] = phi_apply(p, terminal[i]);
     }
 }
+// The same chain with the shade kernel's shortcut: at a non-primary level whose value A_d + clamp(0, 5, .) lies in [A_d, A_d + 5],
+// if the map composed so far takes the same value at both ends the path ends there with that value.  out_depth = the level
+// at which it settled, -1 if it never did.
+void hc_phi_chain_settled(const float *levels, const float *terminal, long n, int depth, float *out_phi, int *out_depth) {
+    for (long i = 0; i < n; ++i) {
+        Phi p; p.M = 1.f; p.K = 0.f; p.L = -INFINITY; p.U = INFINITY;
+        out_depth[i] = -1;
+        bool done = false;
+        for (int d = 0; d < depth && !done; ++d) {
+            const float A = levels[(i * depth + d) * 2];
+            if (d > 0) {
+                const float lo = phi_apply(p, A), hi = phi_apply(p, A + 5.f);
+                if (lo == hi) { out_phi[i] = lo; out_depth[i] = d; done = true; break; }
+            }
+            p = phi_compose(p, A, levels[(i * depth + d) * 2 + 1]);
+        }
+        if (!done) out_phi[i] = phi_apply(p, terminal[i]);
+    }
+}
 void hc_camera_rays(const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count, unsigned long long seed,
                     float *o, float *d) {
     Camera c = make_camera(cam);

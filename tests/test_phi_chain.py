@@ -93,3 +93,28 @@ def test_depth_zero_is_the_identity_including_nan():
     term = np.array([0.0, -1.5, 7.25, np.nan, np.inf], np.float32)
     got = run(np.zeros((5, 0, 2), np.float32), term)
     assert np.array_equal(np.isnan(got), np.isnan(term)) and np.array_equal(got[~np.isnan(term)], term[~np.isnan(term)])
+
+
+def test_settled_paths_end_early_with_the_same_bits():
+    """shade_kernel ends a path at a level d >= 1 when the map composed so far takes the same value at A_d and at A_d + 5 (the
+    level's value lies in between whatever follows).  The result must be the bits the full chain gives, for ordinary, negative,
+    zero, infinite and NaN factors and terminals, and the shortcut must actually fire on chains with brightly lit vertices."""
+    rng = np.random.RandomState(9)
+    n, depth = 40000, 6
+    A = np.clip(rng.exponential(3.0, (n, depth)), 0, 15).astype(np.float32)
+    A[rng.rand(n, depth) < 0.3] = 0
+    f = (rng.exponential(1.2, (n, depth)) * np.where(rng.rand(n, depth) < 0.1, -1, 1)).astype(np.float32)
+    f[rng.rand(n, depth) < 0.05] = 0
+    f[rng.rand(n, depth) < 0.03] = np.inf
+    f[rng.rand(n, depth) < 0.03] = np.nan
+    term = rng.normal(1.0, 3.0, n).astype(np.float32)
+    term[rng.rand(n) < 0.05] = np.nan
+    term[rng.rand(n) < 0.02] = np.inf
+    lv = np.ascontiguousarray(np.stack([A, f], -1), np.float32)
+    full = run(lv, term)
+    out = np.zeros(n, np.float32)
+    where = np.zeros(n, np.int32)
+    S.hc_lib().hc_phi_chain_settled(S.fp(lv), S.fp(np.ascontiguousarray(term)), C.c_long(n), depth, S.fp(out), S.ip(where))
+    same = (out.view(np.uint32) == full.view(np.uint32)) | (np.isnan(out) & np.isnan(full))
+    assert same.all(), f"{(~same).sum()} chains differ"
+    assert (where >= 1).mean() > 0.2, (where >= 1).mean()
