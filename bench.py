@@ -355,7 +355,9 @@ def run_ours(args):
             "config": {"workload": workload_name(args), "spp_per_gpu_per_step": S_step, "spp_per_step": spp_total,
                        "parallelism": f"spp-split x{world}, one NCCL reduce of the fp32 frame per step" if world > 1 else "single GPU",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); queue buffers exceed L2",
-                       "ray_definition": "rays the reference algorithm needs, per wavelength path (SURVEY 8d)"},
+                       "ray_definition": "rays the reference algorithm needs, per wavelength path (SURVEY 8d): the shadow rays of light samples that are "
+                                         "proven to contribute exactly zero are counted (the reference traces them) but not traced here; "
+                                         "traced_rays_per_s_M is what the GPU really traces, spp_per_s needs no ray definition"},
             "spp_per_s": spp_per_s,
             "mpaths_per_s": paths_step * world * K / (gpu_ms_max * 1e-3) / 1e6,
             "projected_s_2048spp": 2048.0 * pix / spp_per_s,
