@@ -5,16 +5,19 @@
 // a queue of rays that moves through these kernels once per bounce:
 //
 //   generate   tops the queue up with camera rays (path regeneration)   (Renderer.cpp:39-76)
-//   extend     closest hit of every queued ray                          (Scene::intersect)
+//   extend     closest hit of every queued ray, four-wide walk          (Scene::intersect)
 //   light      files every ray under terminal / material type x survives-roulette; one record per vertex
-//   nee        one lane per light sample: draws it, answers the "hit within EPSILON of dist" half of
-//              the visibility test from the light neighbourhood table, queues the rest as shadow rays
+//              that a light can reach (vertices whose every light sample would add exactly zero get none)
+//   nee        one lane per light sample: draws it, drops it when its summand is exactly zero, answers the
+//              "hit within EPSILON of dist" half of the visibility test from the light neighbourhood table,
+//              queues the rest as shadow rays
 //   shadow     occluder search for the queued shadow rays               (Scene.cpp:72-75)
 //   lit        compacts the accepted samples
 //   nee_eval   one lane per accepted sample: the direct-light summand   (Scene.cpp:76-79)
 //   terminal   rays that missed or hit an emitter                       (Scene.cpp:88-107,145-148)
 //   shade<T,C> the rest of castRay for one vertex on material type T: microfacet normal, Fresnel,
 //              sum of the direct-light terms, and (C) reflect/refract choice + continuation rays
+//              (not emitted for paths whose pixel value is already settled by a saturated clamp)
 //
 // A queued ray carries up to three wavelength paths (R, G, B: Renderer.cpp:77-79) that still
 // share their geometry; they read the same sample stream, so they stay together until a
@@ -25,7 +28,8 @@
 //
 // Queues are SoA float4 arrays; appends are combined per block in shared memory (ballot/popc
 // and shuffle scans inside the warp) so each block issues one atomic per counter.  Counts stay
-// on the device; the host reads one 16-byte counter per bounce to size the next launch.
+// on the device, including the plan of the next top-up; the host issues one bounce ahead of the
+// counters it reads back.  terminal and the shade variants run side by side on three side streams.
 // There is no CPU path in this library.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
