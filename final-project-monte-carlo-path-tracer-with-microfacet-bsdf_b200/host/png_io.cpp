@@ -68,7 +68,8 @@ int b2pt_host_write_png_rgba8(const char *path, const unsigned char *rgba, int w
     }
     uLongf zn = compressBound((uLong)raw.size());
     std::vector<unsigned char> z(zn);
-    if (compress2(z.data(), &zn, raw.data(), (uLong)raw.size(), 6) != Z_OK) { set_error("write_png: deflate failed"); return -1; }
+    // level 3: 0.07 s instead of 0.16 s for a 1080p frame at +10 % file size (the render itself takes 1.2 s)
+    if (compress2(z.data(), &zn, raw.data(), (uLong)raw.size(), 3) != Z_OK) { set_error("write_png: deflate failed"); return -1; }
     std::vector<unsigned char> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     unsigned char ihdr[13];
     ihdr[0] = (unsigned char)(width >> 24); ihdr[1] = (unsigned char)(width >> 16); ihdr[2] = (unsigned char)(width >> 8); ihdr[3] = (unsigned char)width;
