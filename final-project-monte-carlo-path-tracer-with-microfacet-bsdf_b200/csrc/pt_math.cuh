@@ -941,12 +941,118 @@ PT_HD_NI float mat_eval(const Material &m, f3 wi, f3 wo, f3 N, int c, float u, f
     return (float)(1. - (double)mat_fresnel(m, -wi, N, c));
 }
 
+// ---- atan2f / acosf as the reference's C library computes them ---------------------------------------------------
+// Scene::sampleEnv calls std::atan2(float, float) and std::acos(float) (src/Scene.hpp:66-67), i.e. glibc's atan2f and
+// acosf.  Those are a third-party dependency of the reference (glibc 2.39 in this image: sysdeps/ieee754/flt-32/
+// {e_atan2f,s_atanf,e_acosf}.c, the fdlibm float routines — plain float arithmetic in a fixed order, no FMA, no ifunc
+// variants).  CUDA's atan2f / acosf are different polynomials and move the texel position by ~1e-4, so the published
+// algorithm is restated here operation for operation (constants as bit patterns); tests/test_cpu_math.py checks the host
+// compile of these functions against the C library bit for bit (every float for atanf / acosf, 2e8 pairs for atan2f), and the
+// device runs the same float operations (-fmad=false, IEEE division and square root).
+PT_HD float atanf_ref(float x) {
+    const uint32_t hx = f2u(x), ix = hx & 0x7fffffffu;
+    const bool neg = (hx >> 31) != 0;
+    const float hi3 = u2f(0x3fc90fdau), lo3 = u2f(0x33a22168u);
+    if (ix >= 0x4c000000u) {  // |x| >= 2^25
+        if (ix > 0x7f800000u) return x + x;
+        return neg ? -hi3 - lo3 : hi3 + lo3;
+    }
+    int id;
+    float hi = 0.f, lo = 0.f;
+    if (ix < 0x3ee00000u) {  // |x| < 0.4375
+        if (ix < 0x31000000u) return x;  // |x| < 2^-29
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000u) {      // |x| < 1.1875
+            if (ix < 0x3f300000u) {  // 7/16 <= |x| < 11/16
+                id = 0; x = (2.0f * x - 1.0f) / (2.0f + x);
+                hi = u2f(0x3eed6338u); lo = u2f(0x31ac3769u);
+            } else {                 // 11/16 <= |x| < 19/16
+                id = 1; x = (x - 1.0f) / (x + 1.0f);
+                hi = u2f(0x3f490fdau); lo = u2f(0x33222168u);
+            }
+        } else if (ix < 0x401c0000u) {  // |x| < 2.4375
+            id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x);
+            hi = u2f(0x3f7b985eu); lo = u2f(0x33140fb4u);
+        } else {
+            id = 3; x = -1.0f / x;
+            hi = hi3; lo = lo3;
+        }
+    }
+    const float z = x * x, w = z * z;
+    const float s1 = z * (u2f(0x3eaaaaabu) + w * (u2f(0x3e124925u) + w * (u2f(0x3dba2e6eu) + w * (u2f(0x3d886b35u) + w * (u2f(0x3d4bda59u) + w * u2f(0x3c8569d7u))))));
+    const float s2 = w * (u2f(0xbe4ccccdu) + w * (u2f(0xbde38e38u) + w * (u2f(0xbd9d8795u) + w * (u2f(0xbd6ef16bu) + w * u2f(0xbd15a221u)))));
+    if (id < 0) return x - x * (s1 + s2);
+    const float r = hi - ((x * (s1 + s2) - lo) - x);
+    return neg ? -r : r;
+}
+PT_HD float atan2f_ref(float y, float x) {
+    const float tiny = u2f(0x0da24260u), pi_o_2 = u2f(0x3fc90fdbu), pi = u2f(0x40490fdbu), pi_lo = u2f(0xb3bbbd2eu), pi_o_4 = u2f(0x3f490fdbu);
+    const uint32_t hx = f2u(x), hy = f2u(y), ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    if (ix > 0x7f800000u || iy > 0x7f800000u) return x + y;
+    if (hx == 0x3f800000u) return atanf_ref(y);
+    const uint32_t m = (hy >> 31) | ((hx >> 30) & 2u);  // 2 * sign(x) + sign(y)
+    if (iy == 0) return m < 2 ? y : (m == 2 ? pi + tiny : -pi - tiny);
+    if (ix == 0) return (hy >> 31) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000u) {
+        if (iy == 0x7f800000u) return m == 0 ? pi_o_4 + tiny : (m == 1 ? -pi_o_4 - tiny : (m == 2 ? 3.0f * pi_o_4 + tiny : -3.0f * pi_o_4 - tiny));
+        return m == 0 ? 0.0f : (m == 1 ? -0.0f : (m == 2 ? pi + tiny : -pi - tiny));
+    }
+    if (iy == 0x7f800000u) return (hy >> 31) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int k = ((int)iy - (int)ix) >> 23;
+    float z;
+    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+    else if ((hx >> 31) && k < -60) z = 0.0f;
+    else z = atanf_ref(fabsf(y / x));
+    switch (m) {
+    case 0: return z;
+    case 1: return u2f(f2u(z) ^ 0x80000000u);
+    case 2: return pi - (z - pi_lo);
+    default: return (z - pi_lo) - pi;
+    }
+}
+PT_HD float acosf_ref(float x) {
+    const float pi = u2f(0x40490fdau), pio2_hi = u2f(0x3fc90fdau), pio2_lo = u2f(0x33a22168u);
+    const float pS0 = u2f(0x3e2aaaabu), pS1 = u2f(0xbea6b090u), pS2 = u2f(0x3e4e0aa8u), pS3 = u2f(0xbd241146u), pS4 = u2f(0x3a4f7f04u), pS5 = u2f(0x3811ef08u);
+    const float qS1 = u2f(0xc019d139u), qS2 = u2f(0x4001572du), qS3 = u2f(0xbf303361u), qS4 = u2f(0x3d9dc62eu);
+    const uint32_t hx = f2u(x), ix = hx & 0x7fffffffu;
+    if (ix == 0x3f800000u) return (hx >> 31) ? pi + 2.0f * pio2_lo : 0.0f;
+    if (ix > 0x3f800000u) return (x - x) / (x - x);
+    if (ix < 0x3f000000u) {  // |x| < 0.5
+        if (ix <= 0x32800000u) return pio2_hi + pio2_lo;
+        const float z = x * x;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (hx >> 31) {  // x < -0.5
+        const float z = (1.0f + x) * 0.5f;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float s = sqrtf(z);
+        const float r = p / q;
+        const float w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    }
+    const float z = (1.0f - x) * 0.5f;  // x > 0.5
+    const float s = sqrtf(z);
+    const float df = u2f(f2u(s) & 0xfffff000u);
+    const float c = (z - df * df) / (s + df);
+    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float r = p / q;
+    const float w = r * s + c;
+    return 2.0f * (df + w);
+}
+
 // ---- Scene::sampleEnv, src/Scene.hpp:60-99 --------------------------------------------------------------------
 PT_HD f3 env_lookup(const SceneView &S, f3 dir) {
     if (!S.use_env) return mk3(S.bg[0], S.bg[1], S.bg[2]);
     f3 d = normalized(dir);
-    float phi = atan2f(d.z, d.x);
-    float theta = acosf(d.y);
+    float phi = atan2f_ref(d.z, d.x);
+    float theta = acosf_ref(d.y);
     float u = (phi + kPi) / (2.f * kPi);
     float v = theta / kPi;
     u = u - floorf(u);

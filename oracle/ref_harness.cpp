@@ -468,6 +468,36 @@ void ref_render_frame_philox(void *h, int sample_begin, int sample_count, int sp
         g_rng.mode = RNG_MT;
     }
 }
+// The pixel loop of Renderer.cpp:36-80 on the reference's OWN sampling scheme: one free-running mt19937 per OpenMP thread
+// (global.hpp:14,42-53), camera draws and the three castRay calls consuming consecutive, INDEPENDENT draws
+// (Renderer.cpp:77-79) — nothing keyed, nothing shared between R, G and B.  Returns the float frame (what the reference
+// accumulates before its 8-bit PNG) and the per-pixel second moment of the per-sample values, so a test can put
+// confidence intervals around it: this is the statistical yardstick for the GPU's keyed, channel-shared streams.
+void ref_render_frame_free(void *h, int spp, uint32_t seed, int threads, float *mean, float *second_moment) {
+    RefScene *S = (RefScene *)h;
+    CamSetup c = cam_setup(S->scene);
+    int W = c.cam.width, H = c.cam.height;
+    if (threads <= 0) threads = 8;  // PARALLELISM, Renderer.cpp:16
+#pragma omp parallel num_threads(threads)
+    {
+        g_rng.mode = RNG_MT;
+        g_rng.mt.seed(0x9E3779B9u * (uint32_t)(omp_get_thread_num() + 1) + seed);
+        g_rng.mt_seeded = true;
+#pragma omp for schedule(dynamic, 8)
+        for (int m = 0; m < W * H; ++m) {
+            double sum[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
+            for (int k = 0; k < spp; ++k) {
+                Vector3f pos, dir;
+                camera_ray(c, m % W, m / W, pos, dir);
+                for (int ch = 0; ch < 3; ++ch) {
+                    float v = S->scene.castRay(Ray(pos, dir), 0, WL[ch]);
+                    sum[ch] += v; sq[ch] += (double)v * v;
+                }
+            }
+            for (int ch = 0; ch < 3; ++ch) { mean[3 * m + ch] = (float)(sum[ch] / spp); second_moment[3 * m + ch] = (float)(sq[ch] / spp); }
+        }
+    }
+}
 // The reference's own Renderer::Render (free-running mt19937, 8 OpenMP threads, writes the PNG).
 void ref_render_real(void *h, int spp, const char *png_path) {
     RefScene *S = (RefScene *)h;

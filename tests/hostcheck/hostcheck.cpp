@@ -316,4 +316,51 @@ void hc_stream_uniforms(unsigned long long seed, unsigned pixel, unsigned sample
     Stream rs = stream_open((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, tag, dim_begin);
     for (int i = 0; i < count; ++i) out[i] = stream_next(rs);
 }
+// ---- atanf_ref / atan2f_ref / acosf_ref against the C library this image ships (the reference calls std::atan2 / std::acos) ----
+// Returns the number of inputs whose results differ in any bit (NaN results compare equal to NaN results).
+static inline bool same_bits(float a, float b) { return f2u(a) == f2u(b) || (a != a && b != b); }
+// every float with a bit pattern in [first, last], stepping by `stride`
+unsigned long long hc_check_atanf(unsigned first, unsigned last, unsigned stride) {
+    unsigned long long bad = 0;
+    const long long n = ((long long)last - (long long)first) / stride + 1;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long long i = 0; i < n; ++i) {
+        const float x = u2f(first + (unsigned)(i * stride));
+        if (!same_bits(atanf_ref(x), ::atanf(x))) ++bad;
+    }
+    return bad;
+}
+unsigned long long hc_check_acosf(unsigned first, unsigned last, unsigned stride) {
+    unsigned long long bad = 0;
+    const long long n = ((long long)last - (long long)first) / stride + 1;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long long i = 0; i < n; ++i) {
+        const float x = u2f(first + (unsigned)(i * stride));
+        if (!same_bits(acosf_ref(x), ::acosf(x))) ++bad;
+    }
+    return bad;
+}
+// n pseudo-random (y, x) pairs: mode 0 = components of unit vectors (what sampleEnv passes), 1 = arbitrary bit patterns
+unsigned long long hc_check_atan2f(long long n, unsigned seed, int mode) {
+    unsigned long long bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long long i = 0; i < n; ++i) {
+        uint4 w = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0, 0, seed, 0x2545F491u);
+        float y, x;
+        if (mode == 0) {
+            f3 v = mk3((float)(int32_t)w.x, (float)(int32_t)w.y, (float)(int32_t)w.z);
+            if ((w.w & 7u) == 0) v.x = (float)(int32_t)w.x * 1e-6f;   // near the poles / the seam
+            if ((w.w & 56u) == 0) v.z = (float)(int32_t)w.z * 1e-7f;
+            v = normalized(v);
+            y = v.z; x = v.x;
+        } else {
+            y = u2f(w.x); x = u2f(w.y);
+        }
+        if (!same_bits(atan2f_ref(y, x), ::atan2f(y, x))) ++bad;
+    }
+    return bad;
+}
+void hc_atan2f_acosf(const float *y, const float *x, long n, float *at, float *ac) {
+    for (long i = 0; i < n; ++i) { at[i] = atan2f_ref(y[i], x[i]); ac[i] = acosf_ref(y[i]); }
+}
 }

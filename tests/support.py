@@ -105,6 +105,7 @@ def ref_lib():
                                                 C.POINTER(C.c_ulonglong)]
         L.ref_render_frame_philox.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, b2pt.c_float_p]
         L.ref_render_real.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        L.ref_render_frame_free.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, b2pt.c_float_p, b2pt.c_float_p]
         _ref = L
     return _ref
 
@@ -260,6 +261,16 @@ class Ref:
         self.L.ref_render_samples_philox(self.h, ip(px), len(px), sample_begin, sample_count, seed & 0xFFFFFFFF, seed >> 32, fp(out),
                                          C.byref(draws))
         return out
+
+    def render_free(self, spp, seed=1, threads=0):
+        """The reference's pixel loop on its own sampling scheme (free-running mt19937 per thread, independent draws for the
+        three castRay calls): (mean frame, per-pixel variance of one sample), both [H, W, 3]."""
+        cam = self.scene.camera
+        mean = np.zeros((cam.height, cam.width, 3), np.float32)
+        m2 = np.zeros((cam.height, cam.width, 3), np.float32)
+        self.L.ref_render_frame_free(self.h, spp, seed & 0xFFFFFFFF, threads, fp(mean), fp(m2))
+        var = np.maximum(m2.astype(np.float64) - mean.astype(np.float64) ** 2, 0.0)
+        return mean, var
 
     def render_frame(self, sample_begin, sample_count, spp_total, seed=SEED, threads=0, fb=None):
         cam = self.scene.camera

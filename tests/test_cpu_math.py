@@ -232,6 +232,25 @@ def test_env_lookup(world):
         assert (r == 0).all()
 
 
+def test_atan2f_acosf_match_the_c_library():
+    """Scene::sampleEnv calls glibc's atan2f / acosf (src/Scene.hpp:66-67).  pt::atanf_ref / atan2f_ref / acosf_ref restate those
+    routines; here the host compile of them is compared with the C library of this image bit for bit: every float for atanf,
+    every float of [-1, 1] (and a stride of the rest) for acosf, 5e7 + 5e7 pairs for atan2f."""
+    import ctypes as C
+    L = S.hc_lib()
+    for f in (L.hc_check_atanf, L.hc_check_acosf):
+        f.restype = C.c_ulonglong
+        f.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    L.hc_check_atan2f.restype = C.c_ulonglong
+    L.hc_check_atan2f.argtypes = [C.c_longlong, C.c_uint, C.c_int]
+    assert L.hc_check_atanf(0, 0xFFFFFFFF, 1) == 0
+    assert L.hc_check_acosf(0, 0x3F800001, 1) == 0
+    assert L.hc_check_acosf(0x80000000, 0xBF800001, 1) == 0
+    assert L.hc_check_acosf(0, 0xFFFFFFFF, 97) == 0
+    assert L.hc_check_atan2f(50_000_000, 1, 0) == 0  # components of unit vectors, poles and seam over-represented
+    assert L.hc_check_atan2f(50_000_000, 2, 1) == 0  # arbitrary bit patterns (zeros, infinities, NaN, denormals)
+
+
 def test_camera_rays_bit_exact(world):
     name, sc, ref, hc = world
     cam = sc.camera

@@ -144,9 +144,9 @@ def test_env_lookup(ctx, world):
     d = np.random.RandomState(13).normal(size=(50000, 3)).astype(np.float32)
     d[:10] = [[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1], [-1, 0, 1e-8], [-1, 0, -1e-8], [1e-8, 1, 0], [0, -1, 1e-8]]
     g, r = ctx.env_lookup(d), ref.sample_env(d)
-    # atan2f / acosf of the device library differ from glibc by an ulp or two: a texel-space offset of ~1e-4
-    assert np.abs(g - r).max() <= 2e-3
-    assert np.abs(g - r).mean() <= 2e-5
+    # atan2f / acosf are the C library's algorithms restated (pt::atan2f_ref / acosf_ref, bit-exact against glibc on the host:
+    # tests/test_cpu_math.py::test_atan2f_acosf_match_the_c_library), so the texel position is the reference's: SURVEY 8c(4) asks 1e-6
+    assert np.abs(g - r).max() <= 1e-6
 
 
 def test_camera_rays_bit_exact(ctx, world):
