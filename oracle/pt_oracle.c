@@ -389,6 +389,12 @@ static void sample_light(const b2pt_scene_desc *d, lsample_t *s, rng_t *g) {
     }
 }
 
+/* Ray accounting: every closest-hit or visibility query the reference algorithm needs for a path — the primary
+ * ray, the n_dir_sample shadow rays of every shaded vertex, the probe ray of every vertex that survives Russian roulette (the
+ * reference traces the probe twice, Scene.cpp:134 + :87; it is counted once) — and the vertices shaded.  Thread-local, summed by
+ * pto_render_samples_counted. */
+static _Thread_local unsigned long long t_rays, t_vertices;
+
 /* ---- Scene::directLighting, src/Scene.cpp:56-82 ------------------------------------------------------------ */
 static float direct_lighting(const b2pt_scene_desc *d, v3 wo, v3 p, v3 n, float tu, float tv, const b2pt_material *m, int c,
                              int is_reflect, rng_t *g) {
@@ -401,6 +407,7 @@ static float direct_lighting(const b2pt_scene_desc *d, v3 wo, v3 p, v3 n, float 
         float dist = norm(sub(ls.p, p));
         ray_t rl = make_ray(p, ws);
         hit_t h = scene_intersect(d, &rl);
+        t_rays++;
         if (!d->enable_shadow || (h.prim >= 0 && fabs(h.t - dist) < EPSILON))
             l_dir += emit * material_eval(m, ws, wo, n, c, tu, tv, is_reflect) * dot(ws, n) * dot(neg(ws), ls.n) / (dist * dist) / ls.pdf /
                      d->n_dir_sample;
@@ -411,6 +418,7 @@ static float direct_lighting(const b2pt_scene_desc *d, v3 wo, v3 p, v3 n, float 
 /* ---- Scene::castRay, src/Scene.cpp:85-184 ------------------------------------------------------------------ */
 static float cast_ray(const b2pt_scene_desc *d, const ray_t *ray, int depth, int c, rng_t *g) {
     hit_t inter = scene_intersect(d, ray);
+    if (depth == 0) t_rays++;
     if (inter.prim < 0) return comp(sample_env(d, ray->d), c);
     surf_t s = surface_of(d, ray, &inter);
     v3 p = s.p, n = s.n;
@@ -418,6 +426,7 @@ static float cast_ray(const b2pt_scene_desc *d, const ray_t *ray, int depth, int
     v3 wo = neg(ray->d);
     if (depth == 0 && s.emissive) return clampf(0, 1, m->emission[c] * fabsf(dot(wo, n)));
 
+    t_vertices++;
     v3 mfn = material_sample(m, n, g);
     float kr = fresnel(m, ray->d, mfn, c);
     float l_dir = 0, l_ind = 0;
@@ -433,6 +442,7 @@ static float cast_ray(const b2pt_scene_desc *d, const ray_t *ray, int depth, int
     v3 wi = is_reflect ? reflect(wo, mfn) : refract(m, ray->d, mfn, c);
     ray_t r = make_ray(p, wi);
     hit_t probe = scene_intersect(d, &r);
+    t_rays++;
     int probe_emits = probe.prim >= 0 && has_emission(&d->materials[d->prim_material[probe.prim]]);
     if (probe.prim >= 0 && !probe_emits) {
         if (!is_rough(m))  /* isDirac */
@@ -550,6 +560,29 @@ void pto_render_samples(const pto_scene *s, const b2pt_camera *cam, const int *p
             }
         }
     }
+}
+/* The same, also returning the rays the reference algorithm needs for these paths and the vertices it shades. */
+void pto_render_samples_counted(const pto_scene *s, const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count,
+                                uint64_t seed, float *out, unsigned long long *rays, unsigned long long *vertices) {
+    unsigned long long nr = 0, nv = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : nr, nv)
+    for (int q = 0; q < npix; ++q) {
+        int m = pixels[q];
+        t_rays = t_vertices = 0;
+        for (int k = 0; k < sample_count; ++k) {
+            uint32_t sm = (uint32_t)(sample_begin + k);
+            rng_t g = rng_stream(seed, (uint32_t)m, sm, B2PT_STREAM_CAMERA);
+            v3 pos, dir;
+            camera_ray(cam, m % cam->width, m / cam->width, &g, &pos, &dir);
+            ray_t r = make_ray(pos, dir);
+            for (int c = 0; c < 3; ++c) {
+                rng_t gp = rng_stream(seed, (uint32_t)m, sm, B2PT_STREAM_PATH);
+                out[((size_t)q * sample_count + k) * 3 + c] = cast_ray(s->d, &r, 0, c, &gp);
+            }
+        }
+        nr += t_rays; nv += t_vertices;
+    }
+    *rays = nr; *vertices = nv;
 }
 /* Renderer.cpp:36-92 for the whole frame: fb[m] += rgb / spp_total in sample order. */
 void pto_render_frame(const pto_scene *s, const b2pt_camera *cam, int sample_begin, int sample_count, int spp_total, uint64_t seed, float *fb) {

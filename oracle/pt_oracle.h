@@ -28,6 +28,10 @@ void pto_sample_light(const pto_scene *s, const float *u4, long n, float *coords
 void pto_camera_rays(const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count, uint64_t seed, float *o, float *dir);
 void pto_render_samples(const pto_scene *s, const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count,
                         uint64_t seed, float *out);
+/* pto_render_samples plus the ray accounting of SURVEY.md 8d: rays the reference algorithm needs (primary + n_dir_sample shadow
+ * rays per shaded vertex + one probe per surviving vertex), vertices shaded */
+void pto_render_samples_counted(const pto_scene *s, const b2pt_camera *cam, const int *pixels, int npix, int sample_begin, int sample_count,
+                                uint64_t seed, float *out, unsigned long long *rays, unsigned long long *vertices);
 void pto_render_frame(const pto_scene *s, const b2pt_camera *cam, int sample_begin, int sample_count, int spp_total, uint64_t seed, float *fb);
 /* Scene::castRay (src/Scene.cpp:85-184) on explicit rays with scripted uniforms */
 void pto_cast_ray_scripted(const pto_scene *s, const float *o, const float *dir, const int *wl, const float *script, int stride, long n,

@@ -10,37 +10,12 @@ import support as S
 
 b2pt = S.b2pt
 
-_keep = []  # temp dirs that must outlive the scenes
+from b2pt import scenes as _pkg  # noqa: E402  (the scene builders live in the package: bench.py and tools/ use them too)
 
-
-def cornell(width=96, height=96, n_dir=0, rr=-1.0):
-    """DEMO scene of src/main.cpp:99-129 (BASELINE config C1 geometry)."""
-    sc = b2pt.HostScene.demo(width, height)
-    sc.set_render(0, rr, -1, n_dir)
-    return sc.build_tree(), None
-
-
-def chess(width=160, height=90, dof=True, sky=True, quality="low", n_dir=0, fix=0, king="gold_conductor", left="smooth_glass",
-          right="rough_white_conductor", spp=32):
-    """conf.json scene of src/main.cpp:137-316 with the shipped values (BASELINE configs C2/C3/C4)."""
-    tmp = tempfile.TemporaryDirectory(prefix="b2pt_chess_")
-    _keep.append(tmp)
-    run = os.path.join(tmp.name, "build")
-    os.makedirs(run)
-    os.makedirs(os.path.join(tmp.name, "models", "envoMaps"))
-    env_png = None
-    if sky:
-        env_png = S.write_sky_png(os.path.join(tmp.name, "models", "envoMaps", "sky.png"))
-        env = '"../models/envoMaps/sky.png"'
-    else:
-        env = "[0, 0, 0]"
-    conf = os.path.join(run, "conf.json")
-    with open(conf, "w") as f:
-        f.write(S.chess_conf_text(width, height, spp, dof, env, quality, king, left, right))
-    sc = b2pt.HostScene.from_conf(conf, run, fix)
-    if n_dir:
-        sc.set_render(0, -1.0, -1, n_dir)
-    return sc.build_tree(), env_png
+_keep = _pkg._keep
+cornell = _pkg.cornell
+chess = _pkg.chess
+cornell_sweep = _pkg.cornell_sweep
 
 
 def two_triangle_scene():
@@ -112,7 +87,7 @@ def random_scene(seed, width=48, height=36):
     if rng.rand() < 0.5:
         tmp = tempfile.TemporaryDirectory(prefix="b2pt_rand_")
         _keep.append(tmp)
-        env_png = S.write_sky_png(os.path.join(tmp.name, "sky.png"), 64, 32, seed)
+        env_png = _pkg.write_sky_png(os.path.join(tmp.name, "sky.png"), 64, 32, seed)
         sc.load_env_png(env_png)
     else:
         sc.set_background(tuple(rng.uniform(0, 0.3, 3).tolist()))

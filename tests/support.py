@@ -475,51 +475,13 @@ def ref_sphere(c4, o, d):
     return hit, t, co, nn
 
 
-# ---- scenes -------------------------------------------------------------------------------------------
-def synthetic_sky(width=256, height=128, seed=0):
-    """Deterministic RGBA8 equirect sky (blue-to-white gradient + value-noise clouds); sky.png is absent upstream."""
-    rng = np.random.RandomState(seed)
-    coarse = rng.rand(height // 8 + 2, width // 8 + 2)
-    ys, xs = np.mgrid[0:height, 0:width]
-    gy, gx = ys / 8.0, xs / 8.0
-    y0, x0 = gy.astype(int), gx.astype(int)
-    fy, fx = gy - y0, gx - x0
-    n = (coarse[y0, x0] * (1 - fx) + coarse[y0, x0 + 1] * fx) * (1 - fy) + (coarse[y0 + 1, x0] * (1 - fx) + coarse[y0 + 1, x0 + 1] * fx) * fy
-    v = ys / max(height - 1, 1)
-    cloud = np.clip((n - 0.55) * 3.0, 0, 1) * (v < 0.5)
-    r = 0.35 + 0.55 * v + 0.4 * cloud
-    g = 0.55 + 0.40 * v + 0.3 * cloud
-    b = 0.95 * np.ones_like(v)
-    img = np.stack([r, g, b, np.ones_like(v)], -1)
-    return (np.clip(img, 0, 1) * 255).astype(np.uint8)
+# ---- scenes (the builders live in the package: b2pt.scenes) ----------------------------------------------------------
+from b2pt import scenes as _scenes  # noqa: E402
 
-
-def write_sky_png(path, width=256, height=128, seed=0):
-    b2pt.write_png(path, synthetic_sky(width, height, seed), width, height)
-    return path
-
-
-CHESS_CONF = """{
-  "camera": {"width": %(w)d, "height": %(h)d, "fov": 70,
-             "position": [278, 150, -2550], "target": [278, 0, 0], "up": [0, 1, 0],
-             "useDOF": %(dof)s, "focusDistance": 3036.98, "apertureRadius": 10},
-  "renderer": {"spp": %(spp)d, "path": "./output.png", "parrallelism": 8},
-  "scene": {"addDiamond": true, "model_quality": "%(quality)s", "includeShadow": true,
-            "RussianRouletteRate": 0.4, "directLightSample": 32, "envMap": %(env)s,
-            "kingPosition": [0, 0, 0], "kingMaterial": "%(king)s",
-            "soldierLeftRowPosition": [-559, 0, -200], "soldierRightRowPosition": [160, 0, -200],
-            "soldierXSpacing": 0, "soldierYSpacing": 0, "soldierZSpacing": -356, "soldierCountPerRow": 7,
-            "soldierMaterials": [%(soldiers)s],
-            "lightPosition": [278, 1300, 0], "lightBrightness": 100.0,
-            "floorMaterial": "silver_mirror", "floor_isTextured": true, "wallMaterial": "rough_white_conductor"}
-}
-"""
-
-
-def chess_conf_text(w=1920, h=1080, spp=2048, dof=True, env='"../models/envoMaps/sky.png"', quality="low", king="gold_conductor",
-                    left="smooth_glass", right="rough_white_conductor"):
-    soldiers = ", ".join(['"%s"' % left] * 7 + ['"%s"' % right] * 7)
-    return CHESS_CONF % dict(w=w, h=h, spp=spp, dof="true" if dof else "false", env=env, quality=quality, king=king, soldiers=soldiers)
+synthetic_sky = _scenes.synthetic_sky
+write_sky_png = _scenes.write_sky_png
+CHESS_CONF = _scenes.CHESS_CONF
+chess_conf_text = _scenes.chess_conf_text
 
 
 # ---- oracle/pt_oracle.c: the plain-C restatement ----------------------------------------------------------------
@@ -600,6 +562,16 @@ class Restated:
         cam = self.scene.camera
         self.L.pto_render_samples(self.h, C.byref(cam), ip(px), len(px), sample_begin, sample_count, C.c_uint64(seed), fp(out))
         return out
+
+    def render_samples_counted(self, pixels, sample_begin, sample_count, seed=SEED):
+        """(per-sample radiance, rays the reference algorithm needs for these paths — SURVEY 8d — and vertices it shades)."""
+        px = i32(pixels)
+        out = np.zeros((len(px), sample_count, 3), np.float32)
+        cam = self.scene.camera
+        rays, verts = C.c_ulonglong(), C.c_ulonglong()
+        self.L.pto_render_samples_counted(self.h, C.byref(cam), ip(px), len(px), sample_begin, sample_count, C.c_uint64(seed), fp(out),
+                                          C.byref(rays), C.byref(verts))
+        return out, rays.value, verts.value
 
     def render_frame(self, sample_begin, sample_count, spp_total, seed=SEED, fb=None):
         cam = self.scene.camera
