@@ -1293,6 +1293,11 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     // the device has less to give.
     size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : (S.n_dir <= 8 ? (size_t)48 << 20 : (size_t)12 << 20);
     if (wave > total) wave = (size_t)std::max<unsigned long long>(total, 1);
+    // Visibility slots are numbered up to 3 * wave * n_dir and share a 32-bit word with the phase flag of the shadow queue
+    // (bit 31), and the slot counter itself is 32 bits wide: the queue is kept short enough for both.
+    const size_t slot_limit = ((size_t)1 << 31) / (3 * (size_t)S.n_dir) / kBlock * kBlock;
+    if (slot_limit < 2 * (size_t)kBlock) return fail(ctx, B2PT_ERR_INVALID, "n_dir_sample too large for one block of rays");
+    wave = std::min(wave, slot_limit - kBlock);
     wave = (wave + kBlock - 1) / kBlock * kBlock;
     int r = setup_wave(ctx, wave * 3, S.n_dir);
     while (r == B2PT_ERR_OOM && p->max_wave_bundles <= 0 && wave > ((size_t)1 << 20)) {
@@ -1638,6 +1643,7 @@ int b2pt_update_scene_params(b2pt_ctx *ctx, float rr_rate, int enable_shadow, in
         ctx->view.inv_rr = 1 / ctx->view.rr_rate;
     }
     if (enable_shadow >= 0) ctx->view.enable_shadow = enable_shadow;
+    if (n_dir_sample > kMaxLightSamples) return fail(ctx, B2PT_ERR_INVALID, "n_dir_sample above B2PT_MAX_LIGHT_SAMPLES");
     if (n_dir_sample > 0) ctx->view.n_dir = n_dir_sample;
     return B2PT_OK;
 }

@@ -4,7 +4,9 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "b2pt.h"
@@ -30,26 +32,62 @@ struct PackedScene {
 };
 constexpr int kMaxLightNeighbours = 12;
 
+constexpr int kMaxLightSamples = B2PT_MAX_LIGHT_SAMPLES;  // n_dir_sample: keeps visibility slots (rays x n_dir) and their phase bit inside 32 bits
+// Depth of the sibling-pair tree (root = 0) by an explicit walk; -1 when a node is reachable twice or the links loop (a tree
+// visits each of its n nodes once, so more than n visits means a cycle or a shared subtree).
+inline int tree_depth(const b2pt_scene_desc *d) {
+    std::vector<std::pair<uint32_t, int>> stack;
+    stack.push_back({0u, 0});
+    size_t visited = 0;
+    int depth = 0;
+    while (!stack.empty()) {
+        const auto [i, dep] = stack.back();
+        stack.pop_back();
+        if (++visited > d->n_nodes) return -1;
+        depth = std::max(depth, dep);
+        const b2pt_node &n = d->nodes[i];
+        if (n.kind != B2PT_NODE_INTERIOR) continue;
+        stack.push_back({2 * n.a, dep + 1});
+        stack.push_back({2 * n.a + 1, dep + 1});
+    }
+    return depth;
+}
+
+inline bool validate_material(const b2pt_material &m, std::string &err) {
+    // MaterialType has four values (src/Material.hpp:13-18); the kernels file rays under 1 + 2 * type + survives
+    if (m.type < B2PT_SMOOTH_CONDUCTOR || m.type > B2PT_ROUGH_DIELECTRIC) { err = "material type outside 0..3"; return false; }
+    return true;
+}
+
 inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
     if (!d) { err = "scene is NULL"; return false; }
     if (d->n_nodes < 2 || (d->n_nodes & 1u) || !d->nodes) { err = "scene needs an even, non-zero number of nodes"; return false; }
     if (d->n_prims == 0 || !d->prim_v0 || !d->prim_e1 || !d->prim_e2 || !d->prim_v1v2 || !d->prim_normal || !d->prim_uv ||
         !d->prim_material || !d->prim_kind) { err = "scene primitive arrays missing"; return false; }
     if (d->n_materials == 0 || d->n_materials > B2PT_MAX_MATERIALS || !d->materials) { err = "bad material table"; return false; }
+    for (uint32_t i = 0; i < d->n_materials; ++i)
+        if (!validate_material(d->materials[i], err)) return false;
     if (d->n_lights > B2PT_MAX_LIGHTS) { err = "too many lights"; return false; }
-    if (d->max_depth + 2 >= (uint32_t)kStackSize) { err = "tree too deep for the traversal stack"; return false; }
     if (d->use_env_map && (!d->env_rgb || d->env_width == 0 || d->env_height == 0)) { err = "env map enabled without texels"; return false; }
-    if (d->n_dir_sample < 1) { err = "n_dir_sample must be >= 1"; return false; }
+    if (d->n_dir_sample < 1 || d->n_dir_sample > kMaxLightSamples) { err = "n_dir_sample must be in 1..1024"; return false; }
     for (uint32_t i = 0; i < d->n_nodes; ++i) {
         const b2pt_node &n = d->nodes[i];
         if (n.kind == B2PT_NODE_INTERIOR) {
             if (2 * (uint64_t)n.a + 1 >= d->n_nodes) { err = "node child index out of range"; return false; }
         } else if (n.kind == B2PT_NODE_TRIANGLE || n.kind == B2PT_NODE_SPHERE) {
             if (n.a >= d->n_prims) { err = "node primitive index out of range"; return false; }
+            // the walk picks the primitive test from the leaf's kind, the shading kernels from prim_kind: they must agree
+            if (d->prim_kind[n.a] != n.kind) { err = "leaf kind differs from prim_kind of its primitive"; return false; }
         } else if (n.kind != B2PT_NODE_EMPTY) { err = "bad node kind"; return false; }
     }
-    for (uint32_t i = 0; i < d->n_prims; ++i)
+    // the depth the walk stacks must hold is computed here, never taken from the caller (d->max_depth is informational)
+    const int depth = tree_depth(d);
+    if (depth < 0) { err = "node links do not form a tree"; return false; }
+    if (depth >= B2PT_MAX_TREE_DEPTH || depth + 2 >= kStackSize) { err = "tree too deep for the traversal stack (B2PT_MAX_TREE_DEPTH)"; return false; }
+    for (uint32_t i = 0; i < d->n_prims; ++i) {
         if (d->prim_material[i] >= d->n_materials) { err = "primitive material index out of range"; return false; }
+        if (d->prim_kind[i] != B2PT_NODE_TRIANGLE && d->prim_kind[i] != B2PT_NODE_SPHERE) { err = "bad prim_kind"; return false; }
+    }
     for (uint32_t i = 0; i < d->n_light_nodes; ++i) {
         int l = d->light_node_left[i], r = d->light_node_right[i], p = d->light_node_prim[i];
         if (l >= (int)d->n_light_nodes || r >= (int)d->n_light_nodes) { err = "light tree index out of range"; return false; }

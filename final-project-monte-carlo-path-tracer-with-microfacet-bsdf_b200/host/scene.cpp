@@ -398,12 +398,20 @@ b2pt_host_scene *b2pt_host_scene_new(void) {
 void b2pt_host_scene_free(b2pt_host_scene *s) { delete s; }
 
 int b2pt_host_find_material(const b2pt_host_scene *s, const char *name) { return s->find_material(name); }
+// MaterialType has four values (src/Material.hpp:13-18); the reference's switch statements return 0 for anything else, the
+// device code indexes tables with it, so other values are refused here (and again by b2pt_upload_scene).
+static bool material_ok(const b2pt_material *m) {
+    if (!m || m->type < B2PT_SMOOTH_CONDUCTOR || m->type > B2PT_ROUGH_DIELECTRIC) { set_error("material type outside 0..3"); return false; }
+    return true;
+}
 int b2pt_host_add_material(b2pt_host_scene *s, const char *name, const b2pt_material *m) {
     if ((int)s->mats.size() >= B2PT_MAX_MATERIALS) { set_error("too many materials"); return -1; }
+    if (!material_ok(m)) return -1;
     return s->add_material(name, *m);
 }
 int b2pt_host_set_material(b2pt_host_scene *s, int index, const b2pt_material *m) {
     if (index < 0 || index >= (int)s->mats.size()) { set_error("bad material index"); return -1; }
+    if (!material_ok(m)) return -1;
     s->mats[index] = *m;
     s->built = false;
     return 0;

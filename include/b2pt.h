@@ -107,13 +107,16 @@ typedef struct b2pt_scene_desc {
     float rr_rate;               /* Scene::rrRate after setRrRate's min(rr, 0.99) */
     float inv_rr;                /* Scene::invRr = 1 / rrRate                    */
     int32_t enable_shadow;
-    int32_t n_dir_sample;        /* reference default 4 (src/Scene.hpp:28)      */
-    uint32_t max_depth;          /* depth of the spliced tree (root = 0); must be < B2PT_MAX_TREE_DEPTH */
+    int32_t n_dir_sample;        /* reference default 4 (src/Scene.hpp:28); 1 .. B2PT_MAX_LIGHT_SAMPLES */
+    uint32_t max_depth;          /* depth of the spliced tree (root = 0), informational: b2pt_upload_scene walks the tree itself
+                                    and refuses depths >= B2PT_MAX_TREE_DEPTH, links that do not form a tree, material types
+                                    outside 0..3 and leaves whose kind differs from prim_kind of their primitive */
 } b2pt_scene_desc;
 
 #define B2PT_MAX_MATERIALS 64
 #define B2PT_MAX_LIGHTS 16
 #define B2PT_MAX_TREE_DEPTH 40
+#define B2PT_MAX_LIGHT_SAMPLES 1024
 
 /* Camera as Renderer::Render reads it (src/Renderer.cpp:22-29, src/Camera.hpp).
  * orientation is row-major [row][col] with columns (left, new_up, forward);
@@ -182,7 +185,7 @@ int b2pt_set_stream(b2pt_ctx *ctx, void *cuda_stream, int use_external);
  * per-mesh trees, Scene::objects/lightsObjects and the env map become device arrays. */
 int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *scene);
 /* Scene::setRrRate / enableShadow / setDirectLightSample (src/Scene.hpp:110-116) on the uploaded scene;
- * rr_rate < 0, enable_shadow < 0, n_dir_sample <= 0 keep the current value. */
+ * rr_rate < 0, enable_shadow < 0, n_dir_sample <= 0 keep the current value; n_dir_sample > B2PT_MAX_LIGHT_SAMPLES is refused. */
 int b2pt_update_scene_params(b2pt_ctx *ctx, float rr_rate, int enable_shadow, int n_dir_sample);
 
 /* ---- the hot path --------------------------------------------------------------------- */

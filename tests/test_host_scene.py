@@ -194,3 +194,54 @@ def test_demo_png_channel_means():
     fb = np.clip(ref.render_frame(0, 6, 6), 0, 1).mean(axis=(0, 1))
     assert np.allclose(fb, lin, rtol=0.06), (fb, lin)
     ref.close(); sc.close()
+
+
+def test_upload_validation_rejects_what_the_kernels_cannot_index():
+    """b2pt_upload_scene's validator (csrc/pt_pack.hpp, shared with tests/hostcheck): material types outside the four of
+    src/Material.hpp:13-18, leaves whose kind differs from prim_kind, light-sample counts beyond the slot arithmetic and trees
+    deeper than the walk stacks are refused; the depth is computed from the links, not taken from the caller."""
+    sc, _ = scenes.cornell(32, 32)
+    d = sc.desc
+    L = S.hc_lib()
+    L.hc_scene_new.restype = C.c_void_p
+
+    def accepted():
+        h = L.hc_scene_new(C.byref(d))
+        if h:
+            L.hc_scene_free(C.c_void_p(h))
+        return bool(h)
+
+    assert accepted()
+    for bad in (-1, 4, 7, 1 << 20):
+        keep = d.materials[2].type
+        d.materials[2].type = bad
+        assert not accepted()
+        d.materials[2].type = keep
+    keep = d.prim_kind[0]
+    d.prim_kind[0] = 2 if keep == 1 else 1
+    assert not accepted()
+    d.prim_kind[0] = 9
+    assert not accepted()
+    d.prim_kind[0] = keep
+    for bad in (0, -3, 1025):
+        keep = d.n_dir_sample
+        d.n_dir_sample = bad
+        assert not accepted()
+        d.n_dir_sample = keep
+    # a caller-supplied depth is not trusted: lying about it changes nothing ...
+    keep = d.max_depth
+    d.max_depth = 1000
+    assert accepted()
+    d.max_depth = keep
+    # ... and links that loop are caught by the walk
+    root_a = d.nodes[0].a
+    idx = next(i for i in range(2, d.n_nodes) if d.nodes[i].kind == 0)
+    keep = d.nodes[idx].a
+    d.nodes[idx].a = root_a
+    assert not accepted()
+    d.nodes[idx].a = keep
+    assert accepted()
+    # the host assembler refuses such materials too
+    with pytest.raises(RuntimeError):
+        sc.add_material("bad", b2pt.Material(5, (0, 0, 0), 1.5, 0.0, 0.1, (0, 0, 0), 0, 0))
+    sc.close()

@@ -5,8 +5,9 @@ cd /root/repo
 T=$(mktemp -d); mkdir -p $T/build $T/models/envoMaps
 python - <<PY
 import sys
-sys.path.insert(0,'tests')
-import support as S
+sys.path.insert(0,'.')
+import b2pt_loader; b2pt_loader.load()
+from b2pt import scenes as S
 S.write_sky_png('$T/models/envoMaps/sky.png', 2048, 1024)
 open('$T/build/conf.json','w').write(S.chess_conf_text(1920,1080,2048,True))
 PY
