@@ -392,6 +392,19 @@ class Restated:
         return fb
 
 
+def pto_stream_uniforms(seed, pixel, sample, tag, dim_begin, count):
+    """Uniforms of a sample stream from the oracle's own Philox (oracle/b2pt_portable.h)."""
+    out = np.zeros(count, np.float32)
+    pto_lib().pto_stream_uniforms(C.c_uint64(seed), C.c_uint32(pixel), C.c_uint32(sample), C.c_uint32(tag), C.c_uint32(dim_begin), count, fp(out))
+    return out
+
+
+def pto_philox_block(ctr, key):
+    c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+    pto_lib().pto_philox_block(c, k, o)
+    return [int(x) for x in o]
+
+
 def pto_tri(v9, o, d):
     v, o, d = f32(v9).reshape(-1, 9), f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
     hit = np.zeros(len(o), np.int32)

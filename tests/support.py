@@ -43,7 +43,7 @@ def ensure_built():
 
 
 # ---- the two CPU checkers: bindings live next to them in oracle/refbind.py ------------------------------------------
-from oracle.refbind import (PTO_LIB, Ref, Restated, have_ref, pto_lib, pto_tri, ref_box, ref_lib, ref_sphere, ref_tri,  # noqa: E402,F401
+from oracle.refbind import (PTO_LIB, Ref, Restated, have_ref, pto_lib, pto_philox_block, pto_stream_uniforms, pto_tri, ref_box, ref_lib, ref_sphere, ref_tri,  # noqa: E402,F401
                             write_obj_soup)
 
 

@@ -160,10 +160,42 @@ def test_camera_rays_bit_exact(ctx, world):
 
 
 def test_stream_uniforms(ctx):
-    g = ctx.stream_uniforms(S.SEED, 1234, 56, 0, 3, 50)
-    h = S.hc_stream_uniforms(S.SEED, 1234, 56, 0, 3, 50)
-    assert np.array_equal(g, h)
-    assert (g >= 0).all() and (g < 1).all()
+    """Device Philox streams against the ORACLE's own implementation (oracle/b2pt_portable.h, pinned to the published Philox4x32-10
+    known answers by tests/test_oracle.py) — not against a host compile of the device header."""
+    for seed, pixel, sample, tag, dim0, n in ((S.SEED, 1234, 56, 0, 3, 50), (S.SEED, 0, 0, 1, 0, 9), (0xDEADBEEFCAFEF00D, 2073599, 2047, 0, 1021, 40),
+                                              (1, 77, 4095, 1, 2, 7)):
+        g = ctx.stream_uniforms(seed, pixel, sample, tag, dim0, n)
+        o = S.pto_stream_uniforms(seed, pixel, sample, tag, dim0, n)
+        assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+        assert np.array_equal(g, S.hc_stream_uniforms(seed, pixel, sample, tag, dim0, n))
+        assert (g >= 0).all() and (g < 1).all()
+
+
+def test_textured_reflectance(ctx, world):
+    """Material::getReflectance's checkerboard (src/Material.hpp:134-151) through eval on the device: the chess floor is the
+    textured silver mirror (floor_isTextured), Schlick's F0 comes from (u, v).  uv values sit on and around the cell borders."""
+    name, sc, ref = world
+    textured = [i for i, (_, m) in enumerate(sc.materials()) if m.textured]
+    if name == "cornell":
+        assert not textured
+        pytest.skip("no textured material in the DEMO scene")
+    assert textured
+    rng = np.random.RandomState(17)
+    n = 60000
+    wi, wo, nrm, wl, uv, rf = bsdf_inputs(rng, n)
+    wo[: n // 2] = (2 * (wi[: n // 2] * nrm[: n // 2]).sum(1, keepdims=True) * nrm[: n // 2] - wi[: n // 2]).astype(np.float32)  # exact mirror pairs: F is returned
+    rf[:] = 1
+    # uv on the checker's cell borders (col = int((u - .05) * 10), row = int(v * 12)) and outside [0, 1]
+    k = n // 4
+    uv[:k, 0] = (0.05 + rng.randint(-1, 12, k) / 10.0 + rng.choice([-1e-7, 0.0, 1e-7], k)).astype(np.float32)
+    uv[:k, 1] = (rng.randint(-1, 14, k) / 12.0 + rng.choice([-1e-7, 0.0, 1e-7], k)).astype(np.float32)
+    for mat in textured:
+        e_r, e_g = ref.bsdf_eval(mat, wi, wo, nrm, wl, uv, rf), ctx.bsdf_eval(mat, wi, wo, nrm, wl, uv, rf)
+        assert rel_close(e_g, e_r, 1e-5, 1e-7).all()
+        nz = e_r > 0
+        assert nz.mean() > 0.1
+        # both checker values occur (0.9 / 0.1 cells), so the test sees the texture and not a constant F0
+        assert len(np.unique(np.round(e_r[nz], 2))) > 5
 
 
 # ---- (c) radiance per sample on shared sample streams -------------------------------------------------------------

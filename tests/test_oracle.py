@@ -68,3 +68,17 @@ def test_radiance_per_sample(world):
     ok = rel_close(a, b, 1e-5, 1e-7)
     assert ok.all(), f"{name}: {(~ok).sum()} of {ok.size} differ, worst {np.abs(a - b).max()}"
     assert b.mean() > 1e-3
+
+
+def test_philox_known_answers():
+    """The oracle's Philox4x32-10 (oracle/b2pt_portable.h) against the known-answer vectors published with Random123
+    (kat_vectors: philox4x32 10 rounds), and the device header's host compile against the oracle's streams."""
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+           ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+           ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1])]
+    for ctr, key, want in kat:
+        assert S.pto_philox_block(ctr, key) == want
+    for seed, pixel, sample, tag, dim0, n in ((S.SEED, 1234, 56, 0, 3, 50), (0xDEADBEEFCAFEF00D, 2073599, 2047, 1, 1021, 40)):
+        a = S.pto_stream_uniforms(seed, pixel, sample, tag, dim0, n)
+        b = S.hc_stream_uniforms(seed, pixel, sample, tag, dim0, n)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
