@@ -1403,6 +1403,7 @@ struct b2pt_ctx {
     cudaEvent_t done_ev[2] = {nullptr, nullptr};
     cudaEvent_t tev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // extend / shadow timing per ring slot
     DevBuf fb;                  // device accumulation buffer of b2pt_render / b2pt_render_samples
+    long long fb_frame_pixels = 0;  // pixels of the FRAME fb holds (b2pt_render / b2pt_group_render); 0 after anything else wrote to it
     DevBuf pixels;
     std::vector<DevBuf> scratch;
 };
@@ -1905,10 +1906,12 @@ int b2pt_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params 
     if (p && (p->flags & B2PT_FLAG_FRESH_FRAME)) CU(cudaMemsetAsync(ctx->fb.p, 0, bytes, ctx->stream));
     else CU(cudaMemcpyAsync(ctx->fb.p, out_rgb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     RenderJob job{0, nullptr, 0, (float *)ctx->fb.p};
+    ctx->fb_frame_pixels = 0;
     r = run_render(ctx, cam, p, job, stats);
     if (r) return r;
     CU(cudaMemcpyAsync(out_rgb_host, ctx->fb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->fb_frame_pixels = (long long)cam->width * cam->height;
     return B2PT_OK;
 }
 
@@ -1967,6 +1970,7 @@ int b2pt_group_render(b2pt_ctx **ctxs, int n, const b2pt_camera *cam, const b2pt
     std::lock_guard<std::mutex> lock(g_nccl.mu);
     std::string err;
     if (!g_nccl.ensure(devs, err)) return fail(ctx, B2PT_ERR_NCCL, err);
+    for (int i = 0; i < n; ++i) ctxs[i]->fb_frame_pixels = 0;
     const size_t count = (size_t)cam->width * cam->height * 3, bytes = count * sizeof(float);
     // shares: contiguous blocks, the remainder spread over the first contexts
     std::vector<int> rc(n, B2PT_OK);
@@ -2007,6 +2011,7 @@ int b2pt_group_render(b2pt_ctx **ctxs, int n, const b2pt_camera *cam, const b2pt
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(out_rgb_host, ctx->fb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->fb_frame_pixels = (long long)cam->width * cam->height;
     if (stats) {
         *stats = st[0];
         for (int i = 1; i < n; ++i) {
@@ -2031,6 +2036,7 @@ int b2pt_render_samples(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render
     for (int i = 0; i < n_pixels; ++i)
         if (pixels[i] < 0 || pixels[i] >= cam->width * cam->height) return fail(ctx, B2PT_ERR_INVALID, "pixel index out of range");
     size_t count = (size_t)n_pixels * p->sample_count * 3;
+    ctx->fb_frame_pixels = 0;  // fb is about to hold per-sample values, not a frame
     int r = ensure(ctx, ctx->fb, count * sizeof(float));
     if (r) return r;
     r = upload(ctx, ctx->pixels, pixels, (size_t)n_pixels * sizeof(int));
@@ -2291,7 +2297,8 @@ int b2pt_tonemap_rgba8(b2pt_ctx *ctx, const float *rgb_host, int n_pixels, unsig
         CU(cudaMemcpyAsync(d, rgb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
         d_rgb = d;
     } else {  // the frame the last b2pt_render / b2pt_group_render left on this device
-        if (!ctx->fb.p || ctx->fb.bytes < bytes) return fail(ctx, B2PT_ERR_INVALID, "no device-resident frame of that size");
+        if (!ctx->fb.p || ctx->fb.bytes < bytes || ctx->fb_frame_pixels != (long long)n_pixels)
+            return fail(ctx, B2PT_ERR_INVALID, "no device-resident frame of that size (the last call on this context was not a b2pt_render / b2pt_group_render of n_pixels pixels)");
         d_rgb = (const float *)ctx->fb.p;
     }
     const unsigned cap = 1u << 16;

@@ -115,16 +115,42 @@ int main(int argc, char **argv) {
     std::cout << "SPP: " << total_spp << "\n";
     unsigned long long rays = 0;
     double gpu_ms = 0;
-    // checkpoint file: magic, width, height, spp_total, samples done, seed, then the fp32 accumulation (sum_k rgb_k / spp_total)
-    struct CkptHeader { char magic[8]; int32_t width, height, spp_total, done; uint64_t seed; };
+    // checkpoint file: magic, width, height, spp_total, samples done, seed, a hash of everything else the samples depend on
+    // (geometry, materials, lights, environment, camera, rr / shadow / light-sample settings), then the fp32 accumulation
+    // (sum_k rgb_k / spp_total).  A resume with another conf.json, --ndir, --fix-* or --demo is refused instead of mixing
+    // samples of two scenes into one frame.
+    struct CkptHeader { char magic[8]; int32_t width, height, spp_total, done; uint64_t seed, scene_hash; };
+    const uint64_t scene_hash = [&]() {
+        uint64_t hsh = 1469598103934665603ull;  // FNV-1a
+        auto mix = [&](const void *ptr, size_t bytes) {
+            const unsigned char *b = (const unsigned char *)ptr;
+            for (size_t i = 0; i < bytes; ++i) { hsh ^= b[i]; hsh *= 1099511628211ull; }
+        };
+        const b2pt_scene_desc *d = b2pt_host_scene_desc(scene);
+        mix(&d->n_nodes, 4); mix(d->nodes, sizeof(b2pt_node) * (size_t)d->n_nodes);
+        mix(&d->n_prims, 4);
+        mix(d->prim_v0, 16 * (size_t)d->n_prims); mix(d->prim_e1, 16 * (size_t)d->n_prims); mix(d->prim_e2, 16 * (size_t)d->n_prims);
+        mix(d->prim_uv, 24 * (size_t)d->n_prims); mix(d->prim_material, 4 * (size_t)d->n_prims); mix(d->prim_kind, 4 * (size_t)d->n_prims);
+        for (uint32_t i = 0; i < d->n_materials; ++i) {  // field by field: the struct has a padding word
+            const b2pt_material &m = d->materials[i];
+            mix(&m.type, 4); mix(m.emission, 12); mix(&m.ior_a, 4); mix(&m.ior_b, 4); mix(&m.roughness, 4); mix(m.base_reflectance, 12); mix(&m.textured, 4);
+        }
+        mix(&d->n_lights, 4); mix(d->light_root, 4 * (size_t)d->n_lights); mix(d->light_material, 4 * (size_t)d->n_lights);
+        mix(&d->use_env_map, 4); mix(&d->env_width, 4); mix(&d->env_height, 4);
+        if (d->use_env_map) mix(d->env_rgb, 12 * (size_t)d->env_width * d->env_height);
+        mix(d->background, 12); mix(&d->rr_rate, 4); mix(&d->enable_shadow, 4); mix(&d->n_dir_sample, 4);
+        mix(&cam->width, 4); mix(&cam->height, 4); mix(cam->position, 12); mix(cam->orientation, 36); mix(&cam->scale, 4); mix(&cam->aspect, 4);
+        mix(&cam->use_dof, 4); mix(&cam->focal_distance, 4); mix(&cam->aperture_radius, 4);
+        return hsh;
+    }();
     int first_sample = 0;
     if (!resume.empty()) {
         FILE *f = std::fopen(resume.c_str(), "rb");
         CkptHeader h{};
-        if (!f || std::fread(&h, sizeof h, 1, f) != 1 || std::memcmp(h.magic, "B2PTCKP1", 8) != 0 || h.width != cam->width || h.height != cam->height ||
+        if (!f || std::fread(&h, sizeof h, 1, f) != 1 || std::memcmp(h.magic, "B2PTCKP2", 8) != 0 || h.scene_hash != scene_hash || h.width != cam->width || h.height != cam->height ||
             h.spp_total != total_spp || h.seed != seed || h.done < 0 || h.done > total_spp ||
             std::fread(framebuffer.data(), sizeof(float), framebuffer.size(), f) != framebuffer.size()) {
-            std::fprintf(stderr, "cannot resume from %s: missing, truncated, or written for another frame size / spp / seed\n", resume.c_str());
+            std::fprintf(stderr, "cannot resume from %s: missing, truncated, or written for another scene / configuration / frame size / spp / seed\n", resume.c_str());
             return 1;
         }
         std::fclose(f);
@@ -134,7 +160,7 @@ int main(int argc, char **argv) {
         if (checkpoint.empty()) return true;
         const std::string tmp = checkpoint + ".tmp";
         FILE *f = std::fopen(tmp.c_str(), "wb");
-        CkptHeader h{{'B', '2', 'P', 'T', 'C', 'K', 'P', '1'}, cam->width, cam->height, total_spp, done, seed};
+        CkptHeader h{{'B', '2', 'P', 'T', 'C', 'K', 'P', '2'}, cam->width, cam->height, total_spp, done, seed, scene_hash};
         bool ok = f && std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(framebuffer.data(), sizeof(float), framebuffer.size(), f) == framebuffer.size();
         if (f) ok = (std::fclose(f) == 0) && ok;
         ok = ok && std::rename(tmp.c_str(), checkpoint.c_str()) == 0;  // a crash never leaves a half-written checkpoint behind

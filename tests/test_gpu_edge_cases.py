@@ -125,6 +125,12 @@ def test_device_tonemap_is_byte_identical_to_the_host_loop(ctx):
     fb, _ = ctx.render(sc.camera, 4)
     got = ctx.tonemap_rgba8(None, 64 * 48)
     assert np.array_equal(got, b2pt.tonemap_rgba8(fb.reshape(-1, 3)))
+    # ... and nothing else: another size, or per-sample values written by b2pt_render_samples since, are refused
+    with pytest.raises(RuntimeError):
+        ctx.tonemap_rgba8(None, 64 * 47)
+    ctx.render_samples(sc.camera, np.arange(64 * 48, dtype=np.int32), 0, 1)
+    with pytest.raises(RuntimeError):
+        ctx.tonemap_rgba8(None, 64 * 48)
     # a constant frame sitting exactly on a boundary: more ambiguous values than the list holds -> host fallback, still identical
     const = np.full((70000, 3), edge[100], np.float32)
     assert np.array_equal(ctx.tonemap_rgba8(const), b2pt.tonemap_rgba8(const))

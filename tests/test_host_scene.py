@@ -245,3 +245,70 @@ def test_upload_validation_rejects_what_the_kernels_cannot_index():
     with pytest.raises(RuntimeError):
         sc.add_material("bad", b2pt.Material(5, (0, 0, 0), 1.5, 0.0, 0.1, (0, 0, 0), 0, 0))
     sc.close()
+
+
+def _png(width, height, depth, ctype, rows_of, interlace=0, plte=None):
+    """A PNG file image as bytes: rows_of(pass_width, xs, ys, dx, dy, y) -> packed row bytes (filter 0)."""
+    import struct
+    import zlib
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    passes = [(0, 0, 1, 1)] if not interlace else [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+    raw = b""
+    for xs, ys, dx, dy in passes:
+        pw = (width - xs + dx - 1) // dx if width > xs else 0
+        ph = (height - ys + dy - 1) // dy if height > ys else 0
+        if pw == 0 or ph == 0:
+            continue
+        for y in range(ph):
+            raw += b"\x00" + rows_of(pw, xs, ys, dx, dy, y)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, depth, ctype, 0, 0, interlace))
+    if plte is not None:
+        out += chunk(b"PLTE", plte)
+    return out + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
+def test_png_reader_formats_and_hostile_headers(tmp_path):
+    """The env-map decoder (host/png_io.cpp) stands in for lodepng::decode (src/Scene.hpp:39-57): RGBA8 out of any colour type and
+    bit depth, Adam7-interlaced files included; malformed headers are errors, never crashes or exceptions across the C ABI."""
+    rng = np.random.RandomState(3)
+    W, H = 13, 11  # not multiples of 8: the last Adam7 passes are partial
+    img = rng.randint(0, 256, (H, W, 4)).astype(np.uint8)
+
+    def rgba8(pw, xs, ys, dx, dy, y):
+        return img[ys + y * dy, xs:xs + pw * dx:dx].tobytes()
+
+    def rgb16(pw, xs, ys, dx, dy, y):
+        px = img[ys + y * dy, xs:xs + pw * dx:dx, :3].astype(np.uint16)
+        return ((px << 8) | 0x5A).astype(">u2").tobytes()  # lodepng keeps the high byte
+
+    pal = rng.randint(0, 256, (16, 3)).astype(np.uint8)
+    idx = rng.randint(0, 16, (H, W)).astype(np.uint8)
+
+    def pal4(pw, xs, ys, dx, dy, y):
+        v = idx[ys + y * dy, xs:xs + pw * dx:dx]
+        v = np.concatenate([v, np.zeros(len(v) % 2, np.uint8)])
+        return ((v[0::2] << 4) | v[1::2]).astype(np.uint8).tobytes()
+
+    cases = {"rgba8": (8, 6, rgba8, None, img), "rgb16": (16, 2, rgb16, None, np.concatenate([img[..., :3], np.full((H, W, 1), 255, np.uint8)], -1)),
+             "pal4": (4, 3, pal4, pal.tobytes(), np.concatenate([pal[idx], np.full((H, W, 1), 255, np.uint8)], -1))}
+    for name, (depth, ctype, rows, plte, want) in cases.items():
+        for interlace in (0, 1):
+            p = tmp_path / f"{name}_{interlace}.png"
+            p.write_bytes(_png(W, H, depth, ctype, rows, interlace, plte))
+            got = b2pt.read_png(str(p))
+            assert got.shape == (H, W, 4)
+            assert np.array_equal(got, want), (name, interlace)
+    # hostile headers
+    for depth, ctype, w, h in ((0, 6, 4, 4), (3, 2, 4, 4), (8, 5, 4, 4), (8, 6, 0, 4), (8, 6, 0x7FFFFFFF, 0x7FFFFFFF), (16, 3, 4, 4)):
+        p = tmp_path / "bad.png"
+        p.write_bytes(_png(min(w, 4), min(h, 4), 8, 6, lambda pw, *a: bytes(4 * pw)).replace(
+            __import__("struct").pack(">IIBB", min(w, 4), min(h, 4), 8, 6), __import__("struct").pack(">IIBB", w, h, depth, ctype)))
+        with pytest.raises(Exception):
+            b2pt.read_png(str(p))
+    # an env map the reader refuses leaves the scene on its background colour, as Scene::loadEnvMap does
+    sc = b2pt.HostScene.empty()
+    assert sc.load_env_png(str(tmp_path / "bad.png")) != 0
+    sc.close()
