@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                     shaded = true;
                     // light samples are evaluated whether or not shadow rays are traced (Scene.cpp:74) — unless no point of the
                     // lights can contribute to this vertex at all (pt::nee_vertex_is_dead): then it gets no record and no slots
-                    want = !nee_vertex_is_dead(S, m, -r.d, nn, p + nn * kEps);
+                    want = !nee_vertex_is_dead(S, m, -r.d, nn, p + nn * kEps, (info >> INFO_MASK_SHIFT) & 7u);
                 }
             }
         }
@@ -624,10 +624,7 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
                 const Material &m = S.mats[mat];
                 const f3 wo = -r.d;
                 const bool inner = dot(wo, hn) < 0;
-                dead = true;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if ((mask >> c & 1u) && !nee_term_is_zero(m, g, wo, hn, c, !inner)) dead = false;
+                dead = nee_sample_is_dead(m, g, wo, hn, mask, !inner);
             }
             if (dead) vis[i] = 0;
             else {
@@ -1846,6 +1843,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     v.n_lights = (int)d->n_lights;
     for (int k = 0; k < 3; ++k) v.light_c[k] = packed.light_sphere[k];
     v.light_r = packed.light_sphere[3];
+    for (int k = 0; k < 3; ++k) { v.light_bmin[k] = packed.light_box[k]; v.light_bmax[k] = packed.light_box[3 + k]; }
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height;
     v.env = nullptr;
     v.env_tex = 0;

@@ -217,6 +217,7 @@ struct SceneView {
     const float4 *lt_entries;  // light neighbourhood table (pt_pack.hpp): 2 float4 per entry
     const int *lt_off, *lt_cnt;
     float light_c[3], light_r;  // a sphere around every point a light sample can fall on (pt_pack.hpp); light_r < 0: unknown
+    float light_bmin[3], light_bmax[3];  // and an axis-aligned box around them (valid when light_r >= 0)
     int use_env, env_w, env_h;
     const float4 *env;      // texels as float4 (rgb, 0)
     unsigned long long env_tex;  // the same texels as a point-sampled CUDA texture object (device only; 0 = use `env`)
@@ -1182,13 +1183,34 @@ PT_HD NeeGeom nee_geometry(const SceneView &S, f3 p, float u0, float u1, float u
 // The summand of Scene::directLighting is Le * f * cos * cos' / d^2 / pdf / N (below).  When f is the literal 0 and every other
 // factor is finite with non-zero denominators the summand is +-0, and adding it leaves l_dir as it is: such a sample needs
 // neither its visibility test nor its evaluation.  (A non-finite factor would make 0 * x a NaN: those samples are kept.)
-PT_HD bool nee_term_is_zero(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, bool is_reflect) {
+PT_HD bool nee_factors_finite(const NeeGeom &g, f3 n, int c) {
     const float rest = dot(g.ws, n) * dot(-g.ws, g.n_light);
     const float e = comp(g.emit, c);
-    if (!(fabsf(rest) < INFINITY) || !(fabsf(e) < INFINITY) || !(g.dist > 0.f) || !(g.dist < INFINITY) || !(g.dist * g.dist > 0.f) || !(g.pdf > 0.f) ||
-        !(g.pdf < INFINITY))
-        return false;
+    return (fabsf(rest) < INFINITY) && (fabsf(e) < INFINITY) && (g.dist > 0.f) && (g.dist < INFINITY) && (g.dist * g.dist > 0.f) && (g.pdf > 0.f) &&
+           (g.pdf < INFINITY);
+}
+PT_HD bool nee_term_is_zero(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, bool is_reflect) {
+    if (!nee_factors_finite(g, n, c)) return false;
     return mat_eval_returns_zero(m, g.ws, wo, n, c, is_reflect);
+}
+// nee_term_is_zero for every wavelength path in `mask` at once.  Material::eval's zero conditions depend on the wavelength only
+// through the index of refraction of a dielectric's transmission lobe, so the reflection lobe (and any conductor) is decided once.
+PT_HD bool nee_sample_is_dead(const Material &m, const NeeGeom &g, f3 wo, f3 n, uint32_t mask, bool is_reflect) {
+    const bool per_channel = !is_reflect && !mat_is_conductor(m);
+    bool zero_any = false;
+    if (!per_channel) {
+        if (!mat_eval_returns_zero(m, g.ws, wo, n, 0, is_reflect)) return false;
+        zero_any = true;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 3; ++c) {
+        if (!(mask >> c & 1u)) continue;
+        if (!nee_factors_finite(g, n, c)) return false;
+        if (!zero_any && !mat_eval_returns_zero(m, g.ws, wo, n, c, is_reflect)) return false;
+    }
+    return true;
 }
 // The same question for a whole vertex, before any light sample is drawn: can ANY point of the lights give a non-zero
 // summand?  Conservative (never true when a sample could be alive):
@@ -1198,7 +1220,7 @@ PT_HD bool nee_term_is_zero(const Material &m, const NeeGeom &g, f3 wo, f3 n, in
 //  * the reflect lobe of a smooth material wants the half vector within acos(1 - EPSILON) = 0.81 degrees of n, i.e. wi within
 //    1.62 degrees (0.0283 rad) of the mirror direction: nothing if the light sphere stays outside a 0.03 rad cone around it.
 // pn is the point the light samples are aimed from (Scene.cpp:114).  Margins are far above float rounding.
-PT_HD bool nee_vertex_is_dead(const SceneView &S, const Material &m, f3 wo, f3 n, f3 pn) {
+PT_HD bool nee_vertex_is_dead(const SceneView &S, const Material &m, f3 wo, f3 n, f3 pn, uint32_t mask = 7u) {
     if (!(S.light_r >= 0.f)) return false;
     const float won = dot(wo, n);
     if (!(won == won)) return false;
@@ -1209,16 +1231,55 @@ PT_HD bool nee_vertex_is_dead(const SceneView &S, const Material &m, f3 wo, f3 n
     const float d = norm(c);
     if (!(d < INFINITY)) return false;
     if (dot(c, n) + S.light_r * 1.001f < -1e-3f * (d + S.light_r)) return true;
-    if (!mat_is_rough(m) && !inner && d > S.light_r * 1.001f) {
+    {
+        // the same question against the lights' box, a much closer fit for a flat light: the largest n . (P - pn) over the box
+        const float hx = fmaxf(n.x * (S.light_bmin[0] - pn.x), n.x * (S.light_bmax[0] - pn.x));
+        const float hy = fmaxf(n.y * (S.light_bmin[1] - pn.y), n.y * (S.light_bmax[1] - pn.y));
+        const float hz = fmaxf(n.z * (S.light_bmin[2] - pn.z), n.z * (S.light_bmax[2] - pn.z));
+        if (hx + (hy + hz) < -1e-3f * (d + S.light_r)) return true;
+    }
+    if (mat_is_rough(m) || !(d > S.light_r * 1.001f)) return false;
+    const float sa = S.light_r * 1.001f / d, ca = sqrtf(fmaxf(0.f, 1.f - sa * sa));  // angular radius of the light sphere
+    if (!inner) {
         const f3 mdir = n * (2.f * won) - wo;
         const float ml = norm(mdir);
         if (!(ml > 0.5f && ml < 2.f)) return false;
         const float cosang = dot(mdir, c) / (d * ml);
-        const float sa = S.light_r * 1.001f / d, ca = sqrtf(fmaxf(0.f, 1.f - sa * sa));
         const float cos_lim = 0.99955003f * ca - 0.029995501f * sa;  // cos(0.03 + asin(sa))
-        if (cosang < cos_lim - 1e-4f) return true;
+        return cosang < cos_lim - 1e-4f;
     }
-    return false;
+    // Seen from inside a smooth dielectric the samples are asked for the TRANSMISSION lobe (Scene.cpp:117), which Material::eval
+    // keeps only when the half vector -wi - eta wo lies within acos(1 - EPSILON) of n (Material.hpp:395-397), eta = ior for a
+    // light on the outer side.  With |-wi - eta wo| <= 1 + eta that pins the tangential part of wi to within
+    // tau = sqrt(2 EPSILON) (1 + eta) of r_t = -eta wo_t, i.e. wi to a chord tau / cos' around the refracted direction r
+    // (cos' the cosine of the steepest such direction).  The vertex is dead when, for every wavelength path on the ray, that
+    // cone misses the light sphere.  Near the critical angle the cone opens up and the vertex is simply kept.
+    const float wl2 = dot(wo, wo);
+    if (!(wl2 > 0.25f && wl2 < 4.f)) return false;
+    const f3 wot = wo - n * won;  // tangential part of wo (n is unit up to rounding)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int ch = 0; ch < 3; ++ch) {
+        if (!(mask >> ch & 1u)) continue;
+        const float eta = mat_ior(m, ch);
+        if (!(eta > 0.f && eta < 16.f)) return false;
+        const f3 rt = wot * (-eta);
+        const float rt2 = dot(rt, rt);
+        const float tau = 0.0142f * (1.f + eta) * 1.05f;
+        const float edge = sqrtf(rt2) + tau;
+        if (edge > 1.f + tau + tau) continue;   // beyond the critical angle by more than the tolerance: no direction qualifies
+        if (!(edge < 0.93f)) return false;      // grazing refraction: the cone is too wide to bound, keep the vertex
+        const float cosp = sqrtf(1.f - edge * edge);
+        const float k = tau / cosp * 1.02f;      // chord between wi and r
+        const f3 r = rt + n * sqrtf(fmaxf(0.f, 1.f - rt2));
+        const float rl = norm(r);
+        if (!(rl > 0.5f && rl < 2.f)) return false;
+        const float cosal = 1.f - 0.5f * k * k, sinal = k * sqrtf(fmaxf(0.f, 1.f - 0.25f * k * k));
+        const float cos_lim = cosal * ca - sinal * sa;  // cos(alpha + asin(sa))
+        if (!(cosal > 0.5f) || !(dot(r, c) / (d * rl) < cos_lim - 1e-3f)) return false;
+    }
+    return true;
 }
 PT_HD float nee_term(const Material &m, const NeeGeom &g, f3 wo, f3 n, int c, float u, float v, bool is_reflect, int n_dir) {
     float emit = comp(g.emit, c);

@@ -22,6 +22,7 @@ struct PackedScene {
     std::vector<b2pt_node> nodes_fast;  // binned-SAH tree over the same leaves (pt_build.hpp)
     int fast_depth = 0;
     float light_sphere[4] = {0.f, 0.f, 0.f, -1.f};  // centre, radius of a sphere around every light primitive (radius < 0: none)
+    float light_box[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // and the axis-aligned box around them (min, max)
     QuadTree quads;                     // nodes_fast collapsed four-wide; empty when its stack need exceeds kStackSize4
     // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
@@ -204,6 +205,7 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
             if (std::isfinite(r) && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2])) {
                 for (int k = 0; k < 3; ++k) out.light_sphere[k] = (float)c[k];
                 out.light_sphere[3] = (float)r;
+                for (int k = 0; k < 3; ++k) { out.light_box[k] = lb.mn[k]; out.light_box[3 + k] = lb.mx[k]; }
             }
         }
     }

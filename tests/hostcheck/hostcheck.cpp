@@ -60,6 +60,7 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     for (int k = 0; k < 3; ++k) v.light_c[k] = h->packed.light_sphere[k];
     v.light_r = h->packed.light_sphere[3];
+    for (int k = 0; k < 3; ++k) { v.light_bmin[k] = h->packed.light_box[k]; v.light_bmax[k] = h->packed.light_box[3 + k]; }
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height; v.env = h->packed.env.data();
     for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
     v.rr_rate = d->rr_rate; v.inv_rr = d->inv_rr; v.enable_shadow = d->enable_shadow; v.n_dir = d->n_dir_sample;
@@ -225,6 +226,13 @@ void hc_nee_dead(void *h, const float *o, const float *d, const float *u4, long 
             for (int c = 0; c < 3; ++c)
                 if (!nee_term_is_zero(m, g, wo, sf.n, c, !inner)) dead = false;
             if (!dead) ++alive;
+            // the kernel's all-wavelengths form must agree with the per-wavelength one, for every subset of paths on the ray
+            for (uint32_t mask = 1; mask < 8; ++mask) {
+                bool d1 = true;
+                for (int c = 0; c < 3; ++c)
+                    if ((mask >> c & 1u) && !nee_term_is_zero(m, g, wo, sf.n, c, !inner)) d1 = false;
+                if (d1 != nee_sample_is_dead(m, g, wo, sf.n, mask, !inner)) { out_alive[i] = -1000; return; }
+            }
         }
         out_alive[i] = alive;
     }

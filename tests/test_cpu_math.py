@@ -179,6 +179,7 @@ def test_vertex_level_verdict_never_drops_a_live_light_sample(world):
     inside_o = (co[hit] - nn[hit] * np.float32(1e-3)).astype(np.float32)
     O, D = np.concatenate([o, inside_o]), np.concatenate([d, d[:3000][hit]])
     v, a = hc.nee_dead(O, D, 64, rng)
+    assert (a != -1000).all(), "nee_sample_is_dead (all wavelengths at once) disagrees with the per-wavelength predicate"
     has = a >= 0
     assert has.sum() > 1000
     assert not ((v == 1) & (a > 0)).any(), f"{name}: {((v == 1) & (a > 0)).sum()} vertices called dead have live samples"

@@ -74,7 +74,7 @@ def test_checkpoint_resume_and_preview(tmp_path):
     r = run(common + ["--checkpoint", ck, "--stop-after", "4", "--preview-every", "1"], str(build))
     assert r.returncode == 0, r.stderr
     half = b2pt.read_png(str(build / "output.png")).astype(int)
-    assert os.path.getsize(ck) == 32 + 64 * 48 * 3 * 4
+    assert os.path.getsize(ck) == 40 + 64 * 48 * 3 * 4  # header (magic, size, spp, done, seed, scene hash) + fp32 frame
     # the 4-of-8-spp preview is scaled by spp / samples done: about as bright as the whole frame, only noisier
     assert abs(half[..., :3].mean() - whole[..., :3].mean()) < 0.08 * whole[..., :3].mean()
     r = run(common + ["--resume", ck], str(build))
@@ -83,6 +83,9 @@ def test_checkpoint_resume_and_preview(tmp_path):
     assert (np.abs(resumed - whole) <= 1).mean() > 0.999  # atomics order: last-bit differences at most
     # a checkpoint written for another spp is refused
     r = run([EXE, "--demo", "--spp", "16", "--width", "64", "--height", "48", "--resume", ck], str(build))
+    assert r.returncode != 0 and "cannot resume" in r.stderr
+    # ... and so is one written for another scene configuration (here: another light-sample count), instead of mixing the two
+    r = run(common + ["--ndir", "7", "--resume", ck], str(build))
     assert r.returncode != 0 and "cannot resume" in r.stderr
 
 
