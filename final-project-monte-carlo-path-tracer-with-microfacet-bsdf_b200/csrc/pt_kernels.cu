@@ -69,8 +69,7 @@ struct Counters {
     unsigned int n_cur, n_next, n_shadow, n_vis;  // n_shadow: shadow rays queued for traversal; n_vis: visibility slots handed out
     unsigned int n_class[12];
     unsigned int fetch_extend, fetch_shadow;  // dynamic-fetch cursors of the traversal kernels
-    unsigned int n_lit, n_before_gen;         // accepted light samples of this bounce; queue length before this bounce's top-up
-                                              // (the rays behind it are the new camera rays, in generation order: coherent packets)
+    unsigned int n_lit, pad1;                 // accepted light samples of this bounce
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
     unsigned int max_depth, pad2;
     // Generation plan of the next bounce, written by plan_generation (one thread) so that the host never has to know the
@@ -291,139 +290,15 @@ __device__ __noinline__ bool binary_visible(const SceneView &S, const Ray &r, fl
     return T.visible;
 }
 
-// ---- packet walk: 32 coherent rays share one traversal ---------------------------------------------------------------------
-// The camera rays a bounce adds to the queue sit behind the continuing rays in generation order: a run of 32 is an 8 x 4
-// pixel tile of one sample (or 32 samples of one listed pixel), i.e. rays that visit nearly the same nodes.  A warp walks
-// such a run as ONE packet: one node sequence and one stack for the warp (shared memory), every quad fetched once with all
-// lanes reading the same addresses (one L1 wavefront per load instead of one per lane — the per-ray walk is bound by exactly
-// those), every lane testing its own ray.  A child is entered when ANY lane wants it (its own box test passed and the entry
-// is not beyond its own best hit); a lane tests a primitive iff ITS OWN test of the leaf box passes — the reference's
-// criterion (pt_build.hpp) — with the same pruning margin and tie rule as pt::trav4_step, so every lane ends with the bits
-// its own walk would have produced.  Lanes whose rays need the reference topology (pt::ray_needs_reference_tree) sit out.
-#ifndef B2PT_PACKETS
-#define B2PT_PACKETS 1
-#endif
-__device__ __forceinline__ uint32_t nonneg_bits(float t) { return __float_as_uint(fmaxf(t, 0.f)); }  // order-preserving for t >= 0
-template <bool COUNT>
-__device__ __forceinline__ void packet_walk(const SceneView &S, const Ray &r, bool valid, Hit &h, uint2 *stk, TravStats *st) {
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    h.t = 1.7976931348623157e308;
-    h.prim = -1;
-    float bound = INFINITY;
-    int sp = 0;
-    uint32_t quad = 0;
-    for (;;) {
-        const float4 *p = S.nodes4 + 8 * (size_t)quad;  // the same address in every lane
-        const float4 l0 = PT_LDG4(p), h0 = PT_LDG4(p + 1), l1 = PT_LDG4(p + 2), h1 = PT_LDG4(p + 3);
-        const float4 l2 = PT_LDG4(p + 4), h2 = PT_LDG4(p + 5), l3 = PT_LDG4(p + 6), h3 = PT_LDG4(p + 7);
-        if (COUNT && valid) st->nodes += 4;
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        const bool b0 = box_hit(xyz(l0), xyz(h0), r, &t0) && !(t0 > bound);
-        const bool b1 = box_hit(xyz(l1), xyz(h1), r, &t1) && !(t1 > bound);
-        const bool b2 = box_hit(xyz(l2), xyz(h2), r, &t2) && !(t2 > bound);
-        const bool b3 = box_hit(xyz(l3), xyz(h3), r, &t3) && !(t3 > bound);
-        const uint32_t a0 = f2u(l0.w), a1 = f2u(l1.w), a2 = f2u(l2.w), a3 = f2u(l3.w);
-        const unsigned meta = f2u(h0.w) >> 8;  // leaf mask (bits 0-3), sphere mask (bits 4-7): the same in every lane
-        unsigned hit = valid ? ((b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u)) : 0u;
-        unsigned lm = meta & 15u;
-#pragma unroll 1
-        while (lm) {  // leaf children, slot by slot (uniform loop): the lanes that passed the leaf's box test the primitive
-            const unsigned low = lm & (0u - lm);
-            lm ^= low;
-            const float tl = pick4(low, t0, t1, t2, t3);
-            if ((hit & low) && !(tl > bound)) {
-                const uint32_t prim = pick4u(low, a0, a1, a2, a3);
-                double t;
-                if (COUNT) st->prims++;
-                if (prim_hit(S, prim, ((meta >> 4) & low) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t) &&
-                    (t < h.t || (t == h.t && (int)prim > h.prim))) {
-                    h.t = t; h.prim = (int)prim; bound = prune_bound(t);
-                }
-            }
-        }
-        hit &= ~meta & 15u;
-        // interior children: entry distance of the nearest lane that wants each (all ones: nobody does)
-        const uint32_t k0 = __reduce_min_sync(FULL, ((hit & 1u) && !(t0 > bound)) ? nonneg_bits(t0) : 0xFFFFFFFFu);
-        const uint32_t k1 = __reduce_min_sync(FULL, ((hit & 2u) && !(t1 > bound)) ? nonneg_bits(t1) : 0xFFFFFFFFu);
-        const uint32_t k2 = __reduce_min_sync(FULL, ((hit & 4u) && !(t2 > bound)) ? nonneg_bits(t2) : 0xFFFFFFFFu);
-        const uint32_t k3 = __reduce_min_sync(FULL, ((hit & 8u) && !(t3 > bound)) ? nonneg_bits(t3) : 0xFFFFFFFFu);
-        unsigned want = (k0 != 0xFFFFFFFFu ? 1u : 0u) | (k1 != 0xFFFFFFFFu ? 2u : 0u) | (k2 != 0xFFFFFFFFu ? 4u : 0u) | (k3 != 0xFFFFFFFFu ? 8u : 0u);
-        if (want) {
-            // nearest first, the others on the warp's stack with their keys
-            unsigned bm = want & (0u - want);
-            uint32_t kb = pick4u(want, k0, k1, k2, k3);
-            if ((want & 2u) && k1 < kb) { bm = 2u; kb = k1; }
-            if ((want & 4u) && k2 < kb) { bm = 4u; kb = k2; }
-            if ((want & 8u) && k3 < kb) { bm = 8u; kb = k3; }
-            quad = pick4u(bm, a0, a1, a2, a3);
-            want ^= bm;
-            if (want) {
-                if (lane == 0) {
-                    int q = sp;
-                    if (want & 1u) stk[q++] = make_uint2(a0, k0);
-                    if (want & 2u) stk[q++] = make_uint2(a1, k1);
-                    if (want & 4u) stk[q++] = make_uint2(a2, k2);
-                    if (want & 8u) stk[q++] = make_uint2(a3, k3);
-                }
-                sp += __popc(want);
-                __syncwarp();
-            }
-            continue;
-        }
-        // pop: skip subtrees that lie beyond every lane's best hit
-        const uint32_t far_bits = __reduce_max_sync(FULL, valid ? __float_as_uint(bound) : 0u);
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            const uint2 e = stk[sp];
-            if (e.y <= far_bits) { quad = e.x; found = true; break; }
-        }
-        if (!found) break;
-    }
-}
-
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
                                                         const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
                                                         unsigned *__restrict__ next, int *__restrict__ hit_prim, float *__restrict__ hit_t,
-                                                        Counters *cnt, int packets) {
-    const unsigned n_all = *n_ptr;
+                                                        Counters *cnt) {
+    const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long refs = 0;
     TravStats st{0, 0};
-    // ---- phase A: the rays this bounce generated, in packets of 32 (static round-robin over the warps) ----
-    unsigned n = n_all;  // rays [0, n) are walked one by one in phase B
-#if B2PT_PACKETS
-    if (packets && S.nodes4 != nullptr) {
-        __shared__ uint2 s_stk[kWarps][kStackSize4];
-        n = min(cnt->n_before_gen, n_all);
-        const unsigned n_pk = n_all - n;
-        const unsigned warps = gridDim.x * kWarps, w = blockIdx.x * kWarps + (threadIdx.x >> 5);
-        for (unsigned base = w * 32u; base < n_pk; base += warps * 32u) {
-            const unsigned idx = n + base + lane;
-            const bool valid = base + lane < n_pk;
-            Ray r;
-            r.o = r.d = r.inv = mk3(0, 0, 0);
-            bool own_walk = false;
-            if (valid) {
-                const float4 o = qo[idx], d = qd[idx];
-                r = make_ray(xyz(o), xyz(d));
-                refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                own_walk = ray_needs_reference_tree(r);
-            }
-            Hit h;
-            packet_walk<COUNT>(S, r, valid && !own_walk, h, s_stk[threadIdx.x >> 5], &st);
-            if (own_walk) binary_walk<COUNT>(S, r, &h, &st);
-            if (valid) {
-                hit_prim[idx] = h.prim;
-                hit_t[idx] = (float)h.t;
-            }
-            __syncwarp();
-        }
-    }
-#endif
-    // ---- phase B: everything else, one walk per lane with dynamic refill ----
     bool has = false, exhausted = false;
     unsigned idx = 0;
     Ray r;
@@ -441,13 +316,13 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
                 float4 o = qo[idx], d = qd[idx];
                 r = make_ray(xyz(o), xyz(d));
                 refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
                     Hit h;
                     binary_walk<COUNT>(S, r, &h, &st);
                     hit_prim[idx] = h.prim;
                     hit_t[idx] = (float)h.t;
                 } else {
-                    trav4_begin(T);
+                    trav4_begin(T, r);
                     has = true;
                 }
             }
@@ -644,13 +519,13 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
 
 // ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
 #ifndef B2PT_SHADOW_WIDE
-#define B2PT_SHADOW_WIDE 0
+#define B2PT_SHADOW_WIDE 1  // the padded four-wide walk (one FMA per plane); 0: the binary walk with the reference's arithmetic
 #endif
 #if B2PT_SHADOW_WIDE
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
                                                         const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
-                                                        unsigned char *__restrict__ vis, Counters *cnt, int /*packets*/) {
+                                                        unsigned char *__restrict__ vis, Counters *cnt) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     TravStats st{0, 0};
@@ -675,10 +550,10 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
                 const uint32_t tag = __float_as_uint(d.w);
                 const int phase = (tag & 0x80000000u) ? 1 : 2;
                 slot = tag & 0x7FFFFFFFu;
-                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
                     vis[slot] = binary_visible<COUNT>(S, r, dist, phase, &st) ? 1 : 0;
                 } else {
-                    shadow4_begin(T, dist, phase);
+                    shadow4_begin(T, r, dist, phase);
                     has = true;
                 }
             }
@@ -703,123 +578,13 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
     }
 }
 #else
-// Occluder search (phase 2 of pt::shadow_step) for 32 consecutive entries of the shadow queue as one packet: they are the
-// surviving light samples of one vertex or of neighbouring vertices, all aimed at the same light — one node sequence, one
-// stack, every quad fetched once for the warp.  A lane drops out as soon as it has found an occluder; the packet ends when
-// every lane has.  Each lane tests a primitive iff its own test of the leaf box passes, so each decision is the one its own
-// walk takes.  Returns "no hit with t < dist outside the window" for this lane's ray.
-template <bool COUNT>
-__device__ __forceinline__ bool shadow_packet_walk(const SceneView &S, const Ray &r, float dist, bool valid, uint32_t *stk, TravStats *st) {
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    const double eps = (double)kEps, dd = (double)dist;
-    const float hi = dist + (4e-3f + 1e-5f * dist);
-    bool active = valid;
-    int sp = 0;
-    uint32_t quad = 0;
-    for (;;) {
-        const float4 *p = S.nodes4 + 8 * (size_t)quad;
-        const float4 l0 = PT_LDG4(p), h0 = PT_LDG4(p + 1), l1 = PT_LDG4(p + 2), h1 = PT_LDG4(p + 3);
-        const float4 l2 = PT_LDG4(p + 4), h2 = PT_LDG4(p + 5), l3 = PT_LDG4(p + 6), h3 = PT_LDG4(p + 7);
-        if (COUNT && active) st->nodes += 4;
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        const bool b0 = box_hit(xyz(l0), xyz(h0), r, &t0) && !(t0 > hi);
-        const bool b1 = box_hit(xyz(l1), xyz(h1), r, &t1) && !(t1 > hi);
-        const bool b2 = box_hit(xyz(l2), xyz(h2), r, &t2) && !(t2 > hi);
-        const bool b3 = box_hit(xyz(l3), xyz(h3), r, &t3) && !(t3 > hi);
-        const uint32_t a0 = f2u(l0.w), a1 = f2u(l1.w), a2 = f2u(l2.w), a3 = f2u(l3.w);
-        const unsigned meta = f2u(h0.w) >> 8;
-        unsigned hit = active ? ((b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u)) : 0u;
-        unsigned lm = meta & 15u;
-#pragma unroll 1
-        while (lm) {
-            const unsigned low = lm & (0u - lm);
-            lm ^= low;
-            if (hit & low) {
-                const uint32_t prim = pick4u(low, a0, a1, a2, a3);
-                double t;
-                if (COUNT) st->prims++;
-                if (prim_hit(S, prim, ((meta >> 4) & low) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t) && !(fabs(t - dd) < eps) && t < dd) {
-                    active = false;  // a closer hit outside the window: the closest hit fails the test (Scene.cpp:74-75)
-                    hit = 0;
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) break;
-        hit &= ~meta & 15u;
-        const uint32_t k0 = __reduce_min_sync(FULL, (hit & 1u) ? nonneg_bits(t0) : 0xFFFFFFFFu);
-        const uint32_t k1 = __reduce_min_sync(FULL, (hit & 2u) ? nonneg_bits(t1) : 0xFFFFFFFFu);
-        const uint32_t k2 = __reduce_min_sync(FULL, (hit & 4u) ? nonneg_bits(t2) : 0xFFFFFFFFu);
-        const uint32_t k3 = __reduce_min_sync(FULL, (hit & 8u) ? nonneg_bits(t3) : 0xFFFFFFFFu);
-        unsigned want = (k0 != 0xFFFFFFFFu ? 1u : 0u) | (k1 != 0xFFFFFFFFu ? 2u : 0u) | (k2 != 0xFFFFFFFFu ? 4u : 0u) | (k3 != 0xFFFFFFFFu ? 8u : 0u);
-        if (want) {
-            unsigned bm = want & (0u - want);
-            uint32_t kb = pick4u(want, k0, k1, k2, k3);
-            if ((want & 2u) && k1 < kb) { bm = 2u; kb = k1; }
-            if ((want & 4u) && k2 < kb) { bm = 4u; kb = k2; }
-            if ((want & 8u) && k3 < kb) { bm = 8u; kb = k3; }
-            quad = pick4u(bm, a0, a1, a2, a3);
-            want ^= bm;
-            if (want) {
-                if (lane == 0) {
-                    int q = sp;
-                    if (want & 1u) stk[q++] = a0;
-                    if (want & 2u) stk[q++] = a1;
-                    if (want & 4u) stk[q++] = a2;
-                    if (want & 8u) stk[q++] = a3;
-                }
-                sp += __popc(want);
-                __syncwarp();
-            }
-            continue;
-        }
-        if (sp == 0) break;
-        quad = stk[--sp];
-    }
-    return active;
-}
-
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
                                                         const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
-                                                        unsigned char *__restrict__ vis, Counters *cnt, int packets) {
+                                                        unsigned char *__restrict__ vis, Counters *cnt) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     TravStats st{0, 0};
-#if B2PT_PACKETS
-    if (packets && S.nodes4 != nullptr) {
-        __shared__ uint32_t s_stk[kWarps][kStackSize4];
-        const unsigned warps = gridDim.x * kWarps, w = blockIdx.x * kWarps + (threadIdx.x >> 5);
-        for (unsigned base = w * 32u; base < n; base += warps * 32u) {
-            const unsigned idx = base + lane;
-            const bool valid = idx < n;
-            Ray r;
-            r.o = r.d = r.inv = mk3(0, 0, 0);
-            float dist = 0.f;
-            unsigned slot = 0;
-            int phase = 2;
-            bool own_walk = false;
-            if (valid) {
-                const float4 o = sh_o[idx], d = sh_d[idx];
-                r = make_ray(xyz(o), xyz(d));
-                dist = o.w;
-                const uint32_t tag = __float_as_uint(d.w);
-                phase = (tag & 0x80000000u) ? 1 : 2;
-                slot = tag & 0x7FFFFFFFu;
-                own_walk = phase == 1 || ray_needs_reference_tree(r);  // window search by traversal (no table entry) / NaN slab products: rare
-            }
-            bool visible = shadow_packet_walk<COUNT>(S, r, dist, valid && !own_walk, s_stk[threadIdx.x >> 5], &st);
-            if (own_walk) visible = binary_visible<COUNT>(S, r, dist, phase, &st);
-            if (valid) vis[slot] = visible ? 1 : 0;
-            __syncwarp();
-        }
-        if (COUNT) {
-            unsigned long long nodes = warp_sum((unsigned long long)st.nodes), prims = warp_sum((unsigned long long)st.prims);
-            if (lane == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
-        }
-        return;
-    }
-#endif
     bool has = false, exhausted = false;
     unsigned idx = 0, slot = 0;  // slot: where the decision goes (sh_base[vertex] + sample)
     float dist = 0.f;
@@ -915,9 +680,10 @@ __global__ void __launch_bounds__(kBlock) nee_eval_kernel(SceneView S, Queue q, 
         Stream rs = stream_open(k0, k1, ps.x, ps.y, STREAM_PATH, __float_as_uint(a.w) + 4u * k);
         float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
         const NeeGeom g = nee_geometry(S, xyz(a), u0, u1, u2, u3);
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            if (mask >> c & 1u) nee_val[3 * (size_t)slot + c] = nee_term(m, g, wo, sf.n, c, sf.u, sf.v, !inner, (int)ndir);
+        const f3 term = nee_term3(m, g, wo, sf.n, sf.u, sf.v, !inner, (int)ndir, mask);  // Material::eval shared by the wavelengths
+        if (mask & 1u) nee_val[3 * (size_t)slot] = term.x;
+        if (mask & 2u) nee_val[3 * (size_t)slot + 1] = term.y;
+        if (mask & 4u) nee_val[3 * (size_t)slot + 2] = term.z;
     }
 }
 
@@ -1098,13 +864,27 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
                         n_emit++;
                     }
                 }
+                // Material::eval / pdf of the continuation (Scene.cpp:139-143): the wavelength paths that reflect share wi, so their
+                // half vector, D, G and pdf are computed once (pt::mat_eval_reflect3, bit-identical to one call per path); paths that
+                // refract have their own direction and go through eval / pdf one by one
+                uint32_t refl_mask = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < rs.nch && refl[j]) refl_mask |= 1u << rs.ch[j];
+                f3 ev_refl = mk3(0.f, 0.f, 0.f);
+                float pdf_refl = 1.f;
+                if (refl_mask) {
+                    ev_refl = mat_eval_reflect3(m, wi_refl, wo, nrm, s.u, s.v, refl_mask);
+                    if (ROUGH) pdf_refl = mat_pdf(m, wi_refl, wo, nrm, 0, true);  // the reflection pdf does not depend on the wavelength
+                }
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     if (j >= rs.nch) continue;
-                    float ev = mat_eval(m, wi[j], wo, nrm, rs.ch[j], s.u, s.v, refl[j]);
-                    float f;
+                    float ev, f;
+                    if (CONDUCTOR || refl[j]) ev = comp(ev_refl, rs.ch[j]);
+                    else ev = mat_eval(m, wi[j], wo, nrm, rs.ch[j], s.u, s.v, false);
                     if (!ROUGH) f = ev * S.inv_rr;  // isDirac
-                    else f = ((ev * cosn) / mat_pdf(m, wi[j], wo, nrm, rs.ch[j], refl[j])) * S.inv_rr;
+                    else f = ((ev * cosn) / ((CONDUCTOR || refl[j]) ? pdf_refl : mat_pdf(m, wi[j], wo, nrm, rs.ch[j], false))) * S.inv_rr;
                     lvl_A[j] = clamp_ref(0.f, 15.f, ldir[j]);
                     lvl_e[j] = ev;
                     lvl_f[j] = f;
@@ -1174,7 +954,6 @@ __device__ void plan_generation(Counters *cnt) {
         g = cnt->wave - n;
         if ((unsigned long long)g > left) g = (unsigned)left;
     }
-    cnt->n_before_gen = n;
     cnt->gen_first = cnt->gen_next;
     cnt->gen_count = g;
     cnt->gen_next += g;
@@ -1380,8 +1159,6 @@ struct b2pt_ctx {
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[kSide] = {nullptr, nullptr, nullptr};
     int n_side = kSide;  // 0: everything on the main stream (B2PT_SIDE_STREAMS=0)
-    int packets = 1;     // new camera rays are walked as packets of 32 (B2PT_PACKET_WALK=0: one walk per ray, for A/B runs)
-    int packets_shadow = 1;  // the shadow queue likewise (B2PT_PACKET_SHADOW=0)
     std::string err;
     bool has_scene = false;
     SceneView view{};
@@ -1571,8 +1348,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         generate_kernel<<<grid_for(gen_open || k < 2 ? wave : 1, ctx, 16), kBlock, 0, st>>>(dcam, gp, qa, dc, &dc->n_cur);
         launches++;
         CU(cudaEventRecord(ctx->tev[ring][0], st));
-        if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc, ctx->packets);
-        else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc, ctx->packets);
+        if (count) extend_kernel<true><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
+        else extend_kernel<false><<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa.o, qa.d, qa.info, &dc->n_cur, &dc->fetch_extend, ctx->wb.hit_prim, ctx->wb.hit_t, dc);
         CU(cudaEventRecord(ctx->tev[ring][1], st));
         launches++; ext_launches++;
         light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vtx_pn, ctx->wb.vtx_ps,
@@ -1588,8 +1365,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
                                                                                 ctx->wb.hit_t, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o, ctx->wb.sh_d, dc, gp.k0, gp.k1);
             launches++;
             CU(cudaEventRecord(ctx->tev[ring][2], st));
-            if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc, ctx->packets_shadow);
-            else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc, ctx->packets_shadow);
+            if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
+            else shadow_kernel<false><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
             CU(cudaEventRecord(ctx->tev[ring][3], st));
             launches++; sh_launches++;
         }
@@ -1753,8 +1530,6 @@ int b2pt_create(b2pt_ctx **out, int device) {
     for (auto &ev : c->fork_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     for (auto &ev : c->join_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("B2PT_SIDE_STREAMS")) c->n_side = std::max(0, std::min((int)b2pt_ctx::kSide, atoi(e)));
-    if (const char *e = getenv("B2PT_PACKET_WALK")) c->packets = atoi(e) != 0;
-    if (const char *e = getenv("B2PT_PACKET_SHADOW")) c->packets_shadow = atoi(e) != 0;
     ok = ok && cudaMalloc((void **)&c->d_cnt, sizeof(Counters)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_ring, 2 * sizeof(Counters)) == cudaSuccess;
@@ -1836,8 +1611,9 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_entries, const float4 *, 19, packed.lt_entries.data(), 16 * packed.lt_entries.size());
     UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
-    UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
-    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.nodes.data(), sizeof(b2pt_node) * packed.quads.nodes.size());
+    UP(leaf, const float4 *, 22, packed.leaf.data(), 16 * packed.leaf.size());
+    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.rows.data(), sizeof(float) * packed.quads.rows.size());
+    v.quad_o_max = packed.quads.o_max;
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;

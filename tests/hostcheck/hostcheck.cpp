@@ -33,8 +33,10 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     pack_scene(d, h->packed, fast, opt);
     h->nodes.resize(2 * h->packed.nodes_fast.size());
     std::memcpy(h->nodes.data(), h->packed.nodes_fast.data(), sizeof(b2pt_node) * h->packed.nodes_fast.size());
-    h->nodes4.resize(2 * h->packed.quads.nodes.size());
-    if (!h->nodes4.empty()) std::memcpy(h->nodes4.data(), h->packed.quads.nodes.data(), sizeof(b2pt_node) * h->packed.quads.nodes.size());
+    if (!h->packed.quads.nodes.empty()) {
+        h->nodes4.resize(h->packed.quads.rows.size() / 4);
+        std::memcpy(h->nodes4.data(), h->packed.quads.rows.data(), sizeof(float) * h->packed.quads.rows.size());
+    }
     h->nodes_ref.resize(2 * h->packed.nodes_ref.size());
     std::memcpy(h->nodes_ref.data(), h->packed.nodes_ref.data(), sizeof(b2pt_node) * h->packed.nodes_ref.size());
     auto cp4 = [&](std::vector<float4> &dst, const float *src) { dst.resize(d->n_prims); std::memcpy(dst.data(), src, 16 * (size_t)d->n_prims); };
@@ -56,7 +58,8 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     v.mats = h->packed.mats.data();
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
     v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
-    v.tri = h->packed.tri.data();
+    v.leaf = h->packed.leaf.data();
+    v.quad_o_max = h->packed.quads.o_max;
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     for (int k = 0; k < 3; ++k) v.light_c[k] = h->packed.light_sphere[k];
     v.light_r = h->packed.light_sphere[3];
@@ -147,6 +150,18 @@ void hc_shadow(void *h, const float *o, const float *d, const float *dist, long 
         TravStats st{0, 0};
         visible[i] = light_visible<false>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st) ? 1 : 0;
     }
+}
+// the same decision by the four-wide walk (what the shadow kernel runs); counts: (boxes, primitives) tested
+void hc_shadow4(void *h, const float *o, const float *d, const float *dist, long n, int *visible, unsigned long long *counts) {
+    const SceneView &S = ((HcScene *)h)->view;
+    unsigned long long nodes = 0, prims = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, prims)
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        visible[i] = light_visible4<true>(S, make_ray(V(o + 3 * i), V(d + 3 * i)), dist[i], &st) ? 1 : 0;
+        nodes += st.nodes; prims += st.prims;
+    }
+    if (counts) { counts[0] = nodes; counts[1] = prims; }
 }
 // as the render path calls it: with the light-tree leaf the sample came from (neighbourhood table first)
 void hc_shadow_lnode(void *h, const float *o, const float *d, const float *dist, const int *lnode, long n, int *visible) {
@@ -370,5 +385,32 @@ unsigned long long hc_check_atan2f(long long n, unsigned seed, int mode) {
 }
 void hc_atan2f_acosf(const float *y, const float *x, long n, float *at, float *ac) {
     for (long i = 0; i < n; ++i) { at[i] = atan2f_ref(y[i], x[i]); ac[i] = acosf_ref(y[i]); }
+}
+// mat_eval_reflect3 / mat_eval3 (Material::eval shared by the wavelength paths) against one mat_eval call per path: number of
+// (input, channel, mask) combinations whose bits differ.  Also mat_pdf's independence of the wavelength for the reflection lobe.
+long hc_check_eval3(void *h, int mat, const float *wi, const float *wo, const float *N, const float *uv, long n) {
+    const Material &m = ((HcScene *)h)->view.mats[mat];
+    long bad = 0;
+    for (long i = 0; i < n; ++i) {
+        const f3 a = V(wi + 3 * i), b = V(wo + 3 * i), nn = V(N + 3 * i);
+        for (int refl = 0; refl < 2; ++refl) {
+            float one[3];
+            for (int c = 0; c < 3; ++c) one[c] = mat_eval(m, a, b, nn, c, uv[2 * i], uv[2 * i + 1], refl != 0);
+            for (uint32_t mask = 1; mask < 8; ++mask) {
+                const f3 t = mat_eval3(m, a, b, nn, uv[2 * i], uv[2 * i + 1], refl != 0, mask);
+                const float got[3] = {t.x, t.y, t.z};
+                for (int c = 0; c < 3; ++c) {
+                    const float want = (mask >> c & 1u) ? one[c] : 0.f;
+                    if (!(f2u(got[c]) == f2u(want) || (got[c] != got[c] && want != want) || (got[c] == 0.f && want == 0.f))) ++bad;
+                }
+            }
+        }
+        const float p0 = mat_pdf(m, a, b, nn, 0, true);
+        for (int c = 1; c < 3; ++c) {
+            const float pc = mat_pdf(m, a, b, nn, c, true);
+            if (!(f2u(pc) == f2u(p0) || (pc != pc && p0 != p0))) ++bad;
+        }
+    }
+    return bad;
 }
 }

@@ -96,6 +96,14 @@ class HostCheck:
         self.L.hc_shadow(self.h, fp(o), fp(d), fp(s), C.c_long(len(o)), ip(vis))
         return vis
 
+    def shadow4(self, o, d, dist, counts=False):
+        """The visibility decision by the four-wide walk of the shadow kernel (pt::light_visible4)."""
+        o, d, s = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3), f32(dist)
+        vis = np.zeros(len(o), np.int32)
+        cnt = (C.c_ulonglong * 2)()
+        self.L.hc_shadow4(self.h, fp(o), fp(d), fp(s), C.c_long(len(o)), ip(vis), cnt)
+        return (vis, (cnt[0], cnt[1])) if counts else vis
+
     def shadow_with_light_node(self, o, d, dist, light_prim):
         o, d, s, lp = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3), f32(dist), i32(light_prim)
         vis = np.zeros(len(o), np.int32)

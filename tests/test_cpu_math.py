@@ -122,6 +122,10 @@ def test_shadow_decision(world):
     got = hc.shadow(p, ws, dist)
     assert np.array_equal(got, want), f"{name}: {(got != want).sum()} of {len(want)} visibility decisions differ"
     assert 0.01 < want.mean() < 0.99
+    # the four-wide walk over the padded quads (what the shadow kernel runs): the same decisions
+    got4, (boxes, prims) = hc.shadow4(p, ws, dist, counts=True)
+    assert np.array_equal(got4, want), f"{name}: {(got4 != want).sum()} of {len(want)} four-wide visibility decisions differ"
+    assert boxes > 0
     # the render path also passes the sampled light triangle (tested first): same decisions
     got2 = hc.shadow_with_light_node(p, ws, dist, hc.sample_light_node(u4))
     assert np.array_equal(got2, want)
@@ -165,6 +169,29 @@ def test_zero_summand_predicate_implies_eval_zero():
         if "smooth" in name or name in ("gold_conductor", "silver_mirror"):
             assert (gate | (f_ref != 0)).mean() > 0.999, name  # nearly every zero of a smooth material is one the predicate names
     ref.close(); hc.close(); sc.close()
+
+
+def test_eval_shared_by_the_wavelengths_is_bit_identical():
+    """pt::mat_eval3 / mat_eval_reflect3 (half vector, D, G computed once for the wavelength paths that share wi: nee_eval and the
+    shade kernels) against one pt::mat_eval call per path, for all nine materials plus a textured one, every subset of paths."""
+    import ctypes as C
+    sc, _ = scenes.cornell(32, 32)
+    mi = sc.find_material("silver_mirror")
+    m = sc.get_material(mi)
+    m.textured = 1
+    tex = sc.add_material("textured_silver", m)
+    m2 = sc.get_material(sc.find_material("rough_white_conductor"))
+    m2.textured = 1
+    tex2 = sc.add_material("textured_rough", m2)
+    sc.build_tree()
+    hc = S.HostCheck(sc)
+    hc.L.hc_check_eval3.restype = C.c_long
+    rng = np.random.RandomState(31)
+    wi, wo, nrm, wl, uv, rf = bsdf_inputs(rng, 30000)
+    for mat in list(range(len(b2pt.NAMED_MATERIALS))) + [tex, tex2]:
+        bad = hc.L.hc_check_eval3(hc.h, mat, S.fp(wi), S.fp(wo), S.fp(nrm), S.fp(uv), C.c_long(len(wi)))
+        assert bad == 0, (mat, bad)
+    hc.close(); sc.close()
 
 
 def test_vertex_level_verdict_never_drops_a_live_light_sample(world):

@@ -45,6 +45,7 @@ def test_scene_cpu(name):
         for a, b in zip(impl.sample_light(g["u4"]), (g["light_p"], g["light_n"], g["light_e"], g["light_pdf"])):
             assert np.array_equal(bits(a), bits(b))
     assert np.array_equal(hc.shadow(g["sh_o"], g["sh_d"], g["sh_dist"]), g["sh_visible"])
+    assert np.array_equal(hc.shadow4(g["sh_o"], g["sh_d"], g["sh_dist"]), g["sh_visible"])
     assert np.array_equal(bits(pto.sample_env(g["env_d"])), bits(g["env_rgb"]))
     assert np.array_equal(bits(hc.env(g["env_d"])), bits(g["env_rgb"]))
     o, d = pto.camera_rays(g["pixels"], 2, 3)
