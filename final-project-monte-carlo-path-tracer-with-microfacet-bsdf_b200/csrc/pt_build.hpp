@@ -16,7 +16,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
-#include <cstring>
 #include <vector>
 
 #include "b2pt.h"
@@ -175,55 +174,11 @@ struct SahBuilder {
 // same as with any other tree over them; a walk needs about half the steps of the binary tree, each step being one
 // 128-byte line, and the primitive tests of the (up to four) leaf children of a step run together.
 struct QuadTree {
-    std::vector<b2pt_node> nodes;  // 4 per quad, root = quad 0 (exact boxes; the form the collapse works on and the CPU tests read)
+    std::vector<b2pt_node> nodes;  // 4 per quad, root = quad 0
     int stack_need = 0;            // entries a depth-first walk can hold at once (<= sum over a path of interior children - 1)
-    // The form the kernels walk (pt::quad_slabs): per quad 8 x 4 floats = one 128-byte line,
-    //   rows 0-5: lo.x, hi.x, lo.y, hi.y, lo.z, hi.z of the four children, PADDED outwards by `pad`
-    //   row 6: the four child words (quad index / primitive id), row 7: leaf mask | sphere mask << 4, then unused
-    // EMPTY slots carry NaN planes (every comparison with them fails).
-    std::vector<float> rows;
-    float pad = 0.f, o_max = 0.f;
+    int depth = 0;                 // quads on the longest root-to-leaf chain minus one (the four-lane walk keeps one stack entry per
+                                   // depth and lane, and carries the depth in six bits of its pop key)
 };
-// Padding of the quads' boxes.  The kernels test them with t' = fma(plane', inv, -fl(o inv)) (far planes: + EPSILON folded into
-// the addend) where the reference computes t = fl(fl(plane - o) inv).  With u = 2^-24, |t' - (plane' - o) inv| <=
-// u |inv| (2|o| + |plane'|) + u |inv| |o| (the addend's two roundings) and |t - (plane - o) inv| <= 2u |inv| (|plane| + |o|),
-// so moving every plane outwards by pad >= u (5 |o| + 3 |plane| + pad) makes each near value <= and each far value >= the
-// reference's for any box inside: the padded test cannot fail where the reference's test of a contained box passes (max / min
-// and the comparisons are monotone).  pad = 2^-21 (o_max + p_max) = 8u (...) covers it for ray origins up to o_max per
-// component; o_max = 16 x the scene's largest coordinate (rays from further away take the exact binary walk).
-inline void make_quads(QuadTree &qt) {
-    float p_max = 1.f;
-    for (const b2pt_node &n : qt.nodes)
-        for (int k = 0; k < 3; ++k) {
-            if (n.bmin[k] == n.bmin[k] && std::fabs(n.bmin[k]) < INFINITY) p_max = std::fmax(p_max, std::fabs(n.bmin[k]));
-            if (n.bmax[k] == n.bmax[k] && std::fabs(n.bmax[k]) < INFINITY) p_max = std::fmax(p_max, std::fabs(n.bmax[k]));
-        }
-    qt.o_max = 16.f * p_max;
-    qt.pad = std::ldexp(qt.o_max + p_max, -21);
-    const size_t nq = qt.nodes.size() / 4;
-    qt.rows.assign(nq * 32, 0.f);
-    for (size_t q = 0; q < nq; ++q) {
-        float *row = &qt.rows[q * 32];
-        uint32_t meta = 0;
-        for (int i = 0; i < 4; ++i) {
-            const b2pt_node &n = qt.nodes[4 * q + i];
-            const uint32_t kind = n.kind & 0xFFu;
-            for (int k = 0; k < 3; ++k) {
-                float lo = NAN, hi = NAN;
-                if (kind != B2PT_NODE_EMPTY) {
-                    lo = std::nextafter(n.bmin[k] - qt.pad, -INFINITY);
-                    hi = std::nextafter(n.bmax[k] + qt.pad, INFINITY);
-                }
-                row[(2 * k) * 4 + i] = lo;
-                row[(2 * k + 1) * 4 + i] = hi;
-            }
-            std::memcpy(&row[24 + i], &n.a, 4);
-            if (kind == B2PT_NODE_TRIANGLE || kind == B2PT_NODE_SPHERE) meta |= 1u << i;
-            if (kind == B2PT_NODE_SPHERE) meta |= 16u << i;
-        }
-        std::memcpy(&row[28], &meta, 4);
-    }
-}
 inline float node_half_area(const b2pt_node &n) {
     float dx = n.bmax[0] - n.bmin[0], dy = n.bmax[1] - n.bmin[1], dz = n.bmax[2] - n.bmin[2];
     if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.f;
@@ -241,7 +196,8 @@ struct QuadCollapser {
         return (int)qt.nodes.size() / 4 - 1;
     }
     // Fills quad q with the collapse of the binary slots in `kids` (1 or 2 to start with); returns its stack need.
-    int fill(int q, std::vector<uint32_t> kids) {
+    int fill(int q, std::vector<uint32_t> kids, int depth = 0) {
+        qt.depth = std::max(qt.depth, depth);
         for (;;) {
             if (kids.size() >= 4) break;
             int best = -1;
@@ -268,7 +224,7 @@ struct QuadCollapser {
                 uint32_t pair = n.a;
                 n.a = (uint32_t)cq;
                 qt.nodes[4 * (size_t)q + i] = n;
-                deepest = std::max(deepest, fill(cq, {2 * pair, 2 * pair + 1}));
+                deepest = std::max(deepest, fill(cq, {2 * pair, 2 * pair + 1}, depth + 1));
             } else {
                 qt.nodes[4 * (size_t)q + i] = n;
             }
@@ -286,6 +242,7 @@ struct QuadCollapser {
     }
     void run() {
         qt.nodes.clear();
+        qt.depth = 0;
         int q = alloc_quad();
         if (bin.empty()) return;
         if (bin[0].kind == B2PT_NODE_INTERIOR) qt.stack_need = fill(q, {2 * bin[0].a, 2 * bin[0].a + 1});

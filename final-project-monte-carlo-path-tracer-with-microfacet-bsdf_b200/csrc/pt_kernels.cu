@@ -290,11 +290,189 @@ __device__ __noinline__ bool binary_visible(const SceneView &S, const Ray &r, fl
     return T.visible;
 }
 
+// ---- four lanes per ray ------------------------------------------------------------------------------------------------
+// ncu (profiles/r01q, r02b) shows the one-lane-per-ray walk bound by the L1 data pipe, not by arithmetic: every lane reads its
+// own 128-byte quad with eight 16-byte loads, i.e. eight L1 wavefronts per lane and step, and halving the box arithmetic
+// (profiles/r02c) changed nothing.  Here a ray is walked by FOUR adjacent lanes, one per child of the quad: lane c loads the
+// 32 bytes of child c (the group's four loads fall into one 128-byte line: two wavefronts per ray and step instead of eight),
+// tests that one box with the reference's arithmetic, tests its own primitive when the child is a leaf whose box passed, and
+// the group agrees on the next quad with two butterfly shuffles.  Children that are not taken are pushed by the lane that
+// owns them onto ITS OWN stack together with their depth; the group pops the deepest pending entry (ties: the nearest), which
+// keeps the depth-first discipline and therefore the stack bound.  The order in which candidates are met differs from the
+// one-lane walk, the set of primitives tested per ray (own leaf box passed, entry not beyond the best hit) and the tie rule
+// (larger primitive id) do not: hits and t are bit-identical (tests/test_gpu_parity.py through b2pt_intersect_batch).
+#ifndef B2PT_COOP
+#define B2PT_COOP 1
+#endif
+#ifndef B2PT_COOP_REFILL
+#define B2PT_COOP_REFILL 5  // new rays are fetched when at most this many of the warp's eight groups are still walking
+#endif
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ uint32_t nonneg_bits(float t) { return __float_as_uint(fmaxf(t, 0.f)); }  // order-preserving for t >= 0
+struct Coop {
+    Hit h;           // best hit so far (identical in the four lanes)
+    float bound;
+    uint32_t quad;   // the quad the group is at
+    int level;       // its depth
+    int sp;          // entries on THIS lane's stack
+    bool has;        // the group is walking a ray
+};
+__device__ __forceinline__ void coop_begin(Coop &C) {
+    C.h.t = 1.7976931348623157e308;
+    C.h.prim = -1;
+    C.bound = INFINITY;
+    C.quad = 0; C.level = 0; C.sp = 0;
+    C.has = true;
+}
+// One step of every walking group of the warp.  Returns (per lane) true when the lane's group has just finished its ray: C.h is
+// the result.  All 32 lanes must call.
+template <bool COUNT>
+__device__ __forceinline__ bool coop_step(const SceneView &S, const Ray &r, Coop &C, uint2 *stk, TravStats *st) {
+    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
+    // my child of the group's quad
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (C.has) {
+        const float4 *p = S.nodes4 + 8 * (size_t)C.quad + 2 * c;
+        lo = PT_LDG4(p); hi = PT_LDG4(p + 1);
+    }
+    float t = 0.f;
+    const bool hit = C.has && box_hit(xyz(lo), xyz(hi), r, &t) && !(t > C.bound);
+    const uint32_t a = f2u(lo.w);
+    const unsigned meta = __shfl_sync(kFull, f2u(hi.w), gl) >> 8;  // slot 0 carries the quad's leaf mask (bits 0-3) and sphere mask (4-7)
+    const unsigned ghit = (__ballot_sync(kFull, hit) >> gl) & 15u;
+    const bool is_leaf = (meta >> c) & 1u;
+    if (COUNT && C.has) st->nodes += 1;
+    // leaf children whose box passed: each lane tests its own primitive, the group keeps the closest (ties: larger id)
+    if (__any_sync(kFull, (ghit & meta & 15u) != 0u)) {
+        double tt = 1.7976931348623157e308;
+        int pr = -1;
+        if (hit && is_leaf) {
+            double t2;
+            if (COUNT) st->prims++;
+            if (prim_hit(S, a, ((meta >> (4 + c)) & 1u) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t2)) { tt = t2; pr = (int)a; }
+        }
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+            const double ot = __shfl_xor_sync(kFull, tt, off);
+            const int op = __shfl_xor_sync(kFull, pr, off);
+            if (ot < tt || (ot == tt && op > pr)) { tt = ot; pr = op; }
+        }
+        if (pr >= 0 && (tt < C.h.t || (tt == C.h.t && pr > C.h.prim))) { C.h.t = tt; C.h.prim = pr; C.bound = prune_bound(tt); }
+    }
+    // interior children still wanted: the group goes to the nearest, the others are pushed by their lanes
+    const bool cand = hit && !is_leaf && !(t > C.bound);
+    const uint32_t key = cand ? ((nonneg_bits(t) & ~3u) | c) : 0xFFFFFFFFu;
+    uint32_t kmin = min(key, __shfl_xor_sync(kFull, key, 1));
+    kmin = min(kmin, __shfl_xor_sync(kFull, kmin, 2));
+    const uint32_t a_next = __shfl_sync(kFull, a, gl + (kmin & 3u));
+    const bool descend = kmin != 0xFFFFFFFFu;
+    if (descend) {
+        if (cand && c != (kmin & 3u)) stk[C.sp++] = make_uint2(a | ((uint32_t)(C.level + 1) << 24), f2u(t));
+        C.quad = a_next;
+        C.level++;
+    }
+    // nothing wanted here: pop the deepest pending entry of the group (its lanes first drop what the bound has overtaken)
+    const bool need_pop = C.has && !descend;
+    bool finished = false;
+    if (__any_sync(kFull, need_pop)) {
+        uint32_t pk = 0, ex = 0;
+        if (need_pop) {
+            while (C.sp > 0 && u2f(stk[C.sp - 1].y) > C.bound) --C.sp;
+            if (C.sp > 0) {
+                const uint2 e = stk[C.sp - 1];
+                ex = e.x;
+                pk = ((e.x >> 24) << 26) | ((0xFFFFFFu - (nonneg_bits(u2f(e.y)) >> 8)) << 2) | (3u - c);
+            }
+        }
+        uint32_t pmax = max(pk, __shfl_xor_sync(kFull, pk, 1));
+        pmax = max(pmax, __shfl_xor_sync(kFull, pmax, 2));
+        const unsigned winner = 3u - (pmax & 3u);
+        const uint32_t wx = __shfl_sync(kFull, ex, gl + winner);
+        if (need_pop) {
+            if (pmax == 0u) {
+                C.has = false;
+                finished = true;
+            } else {
+                if (c == winner) --C.sp;
+                C.quad = wx & 0xFFFFFFu;
+                C.level = (int)(wx >> 24);
+            }
+        }
+    }
+    return finished;
+}
+
+#if B2PT_COOP
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
                                                         const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
                                                         unsigned *__restrict__ next, int *__restrict__ hit_prim, float *__restrict__ hit_t,
-                                                        Counters *cnt) {
+                                                        Counters *cnt, double *__restrict__ hit_t64 = nullptr) {
+    const unsigned n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
+    unsigned long long refs = 0;
+    TravStats st{0, 0};
+    bool exhausted = false;
+    unsigned idx = 0;
+    Ray r;
+    r.o = r.d = r.inv = mk3(0, 0, 0);
+    Coop C;
+    coop_begin(C);
+    C.has = false;
+    uint2 stk[kStackSize4];
+    Fetch F = fetch_begin(n);
+    for (;;) {
+        if (!exhausted) {
+            // the leaders of idle groups take new rays; the index is handed to the other three lanes
+            unsigned got = fetch_rays(F, !C.has && c == 0u, n, next, lane);
+            got = __shfl_sync(kFull, got, gl);
+            if (!C.has && got != 0xFFFFFFFFu) {
+                idx = got;
+                const float4 o = qo[idx], d = qd[idx];
+                r = make_ray(xyz(o), xyz(d));
+                if (c == 0u) refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                    if (c == 0u) {  // rare: the reference's own topology, one lane
+                        Hit h;
+                        binary_walk<COUNT>(S, r, &h, &st);
+                        hit_prim[idx] = h.prim;
+                        hit_t[idx] = (float)h.t;
+                        if (hit_t64) hit_t64[idx] = h.t;
+                    }
+                } else {
+                    coop_begin(C);
+                }
+            }
+            exhausted = F.dry && F.lo >= F.hi;
+        }
+        unsigned act = __ballot_sync(kFull, C.has);
+        if (!act) {
+            if (exhausted) break;
+            continue;
+        }
+        do {
+            if (coop_step<COUNT>(S, r, C, stk, &st) && c == 0u) {
+                hit_prim[idx] = C.h.prim;
+                hit_t[idx] = (float)C.h.t;  // Ray::operator()(double t) converts t to float before use
+                if (hit_t64) hit_t64[idx] = C.h.t;  // the parity entry point wants Intersection::distance itself
+            }
+            act = __ballot_sync(kFull, C.has);
+        } while (act && (exhausted || __popc(act) > 4 * B2PT_COOP_REFILL));
+    }
+    refs = warp_sum(refs);
+    unsigned long long nodes = st.nodes, prims = st.prims;
+    if (COUNT) { nodes = warp_sum(nodes); prims = warp_sum(prims); }
+    if (lane == 0) {
+        if (refs) atomicAdd(&cnt->rays_reference, refs);
+        if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
+    }
+}
+#else
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
+                                                        const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
+                                                        unsigned *__restrict__ next, int *__restrict__ hit_prim, float *__restrict__ hit_t,
+                                                        Counters *cnt, double *__restrict__ hit_t64 = nullptr) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long refs = 0;
@@ -316,13 +494,14 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
                 float4 o = qo[idx], d = qd[idx];
                 r = make_ray(xyz(o), xyz(d));
                 refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
                     Hit h;
                     binary_walk<COUNT>(S, r, &h, &st);
                     hit_prim[idx] = h.prim;
                     hit_t[idx] = (float)h.t;
+                    if (hit_t64) hit_t64[idx] = h.t;
                 } else {
-                    trav4_begin(T, r);
+                    trav4_begin(T);
                     has = true;
                 }
             }
@@ -337,6 +516,7 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
             if (has && !trav4_step<COUNT>(S, r, T, &st)) {
                 hit_prim[idx] = T.h.prim;
                 hit_t[idx] = (float)T.h.t;  // Ray::operator()(double t) converts t to float before use
+                if (hit_t64) hit_t64[idx] = T.h.t;
                 has = false;
             }
             act = __ballot_sync(0xffffffffu, has);
@@ -350,6 +530,8 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
         if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
     }
 }
+
+#endif
 
 // Geometry of the hit the shading kernels need (Intersection::coords / normal).
 __device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int prim, float tf, f3 *p, f3 *n, uint32_t *mat, uint32_t *kind) {
@@ -518,59 +700,145 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
 }
 
 // ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
-#ifndef B2PT_SHADOW_WIDE
-#define B2PT_SHADOW_WIDE 1  // the padded four-wide walk (one FMA per plane); 0: the binary walk with the reference's arithmetic
+// The visibility decision walked by four lanes per shadow ray, like the extend kernel (coop_step): lane c loads and tests child c
+// of the group's quad; leaf children whose box passed are tested by their lanes at once — in the window search (phase 1) any hit
+// inside the window restarts the group as the occluder search, in the occluder search (phase 2) any hit with t < dist outside
+// the window ends it — which is order-independent, so the decision is the one pt::shadow_step takes.
+#ifndef B2PT_COOP_SHADOW
+#define B2PT_COOP_SHADOW 1
 #endif
-#if B2PT_SHADOW_WIDE
+#if B2PT_COOP_SHADOW
+struct CoopShadow {
+    float dist, lo, hi;
+    uint32_t quad;
+    int level, sp, phase;
+    bool has;
+};
+__device__ __forceinline__ void coop_shadow_begin(CoopShadow &C, float dist, int phase) {
+    const float m = 4e-3f + 1e-5f * dist;
+    C.dist = dist; C.lo = dist - m; C.hi = dist + m;
+    C.quad = 0; C.level = 0; C.sp = 0; C.phase = phase;
+    C.has = true;
+}
+// Returns 0 while the group keeps walking (or idles), 1 when it has just finished with "visible", 2 with "not visible".
+template <bool COUNT>
+__device__ __forceinline__ int coop_shadow_step(const SceneView &S, const Ray &r, CoopShadow &C, uint32_t *stk, TravStats *st) {
+    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
+    float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
+    if (C.has) {
+        const float4 *p = S.nodes4 + 8 * (size_t)C.quad + 2 * c;
+        lo4 = PT_LDG4(p); hi4 = PT_LDG4(p + 1);
+    }
+    float t = 0.f, x = 0.f;
+    const bool hit = C.has && box_hit2(xyz(lo4), xyz(hi4), r, &t, &x) && !(t > C.hi) && !(C.phase == 1 && x < C.lo);
+    const uint32_t a = f2u(lo4.w);
+    const unsigned meta = __shfl_sync(kFull, f2u(hi4.w), gl) >> 8;
+    const unsigned ghit = (__ballot_sync(kFull, hit) >> gl) & 15u;
+    const bool is_leaf = (meta >> c) & 1u;
+    if (COUNT && C.has) st->nodes += 1;
+    int result = 0;
+    bool restarted = false;
+    if (__any_sync(kFull, (ghit & meta & 15u) != 0u)) {
+        bool inside_hit = false, occluder = false;
+        if (hit && is_leaf) {
+            double tt;
+            if (COUNT) st->prims++;
+            if (prim_hit(S, a, ((meta >> (4 + c)) & 1u) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &tt)) {
+                const bool inside = fabs(tt - (double)C.dist) < (double)kEps;
+                inside_hit = inside;
+                occluder = !inside && tt < (double)C.dist;
+            }
+        }
+        const unsigned g_in = (__ballot_sync(kFull, inside_hit) >> gl) & 15u, g_oc = (__ballot_sync(kFull, occluder) >> gl) & 15u;
+        if (C.has) {
+            if (C.phase == 1) {
+                restarted = g_in != 0u;  // W holds: restart as the occluder search (below; every lane must reach the shuffles)
+            } else if (g_oc) {  // a closer hit outside the window: the closest hit fails the test (Scene.cpp:74-75)
+                C.has = false;
+                result = 2;
+            }
+        }
+    }
+    const bool cand = C.has && !restarted && hit && !is_leaf;
+    const uint32_t key = cand ? ((nonneg_bits(t) & ~3u) | c) : 0xFFFFFFFFu;
+    uint32_t kmin = min(key, __shfl_xor_sync(kFull, key, 1));
+    kmin = min(kmin, __shfl_xor_sync(kFull, kmin, 2));
+    const uint32_t a_next = __shfl_sync(kFull, a, gl + (kmin & 3u));
+    const bool descend = C.has && !restarted && kmin != 0xFFFFFFFFu;
+    if (descend) {
+        if (cand && c != (kmin & 3u)) stk[C.sp++] = a | ((uint32_t)(C.level + 1) << 24);
+        C.quad = a_next;
+        C.level++;
+    }
+    if (restarted) { C.phase = 2; C.sp = 0; C.quad = 0; C.level = 0; }
+    const bool need_pop = C.has && !restarted && !descend;
+    if (__any_sync(kFull, need_pop)) {
+        uint32_t pk = 0, ex = 0;
+        if (need_pop && C.sp > 0) {
+            ex = stk[C.sp - 1];
+            pk = ((ex >> 24) << 2) | (3u - c);
+        }
+        uint32_t pmax = max(pk, __shfl_xor_sync(kFull, pk, 1));
+        pmax = max(pmax, __shfl_xor_sync(kFull, pmax, 2));
+        const unsigned winner = 3u - (pmax & 3u);
+        const uint32_t wx = __shfl_sync(kFull, ex, gl + winner);
+        if (need_pop) {
+            if (pmax == 0u) {  // nothing left: no occluder (phase 2) / no witness (phase 1)
+                C.has = false;
+                result = C.phase == 2 ? 1 : 2;
+            } else {
+                if (c == winner) --C.sp;
+                C.quad = wx & 0xFFFFFFu;
+                C.level = (int)(wx >> 24);
+            }
+        }
+    }
+    return result;
+}
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
                                                         const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
                                                         unsigned char *__restrict__ vis, Counters *cnt) {
     const unsigned n = *n_ptr;
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
     TravStats st{0, 0};
-    bool has = false, exhausted = false;
-    unsigned idx = 0, slot = 0;  // slot: where the decision goes (sh_base[vertex] + sample)
-    float dist = 0.f;
+    bool exhausted = false;
+    unsigned slot = 0;  // where the decision goes (sh_base[vertex] + sample)
     Ray r;
-    ShadowTrav4 T;
-    uint32_t T_stack[kStackSize4];
-    T.stk = T_stack;
     r.o = r.d = r.inv = mk3(0, 0, 0);
-    shadow4_begin(T, 0.f, 2);
+    CoopShadow C;
+    coop_shadow_begin(C, 0.f, 2);
+    C.has = false;
+    uint32_t stk[kStackSize4];
     Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
-            const unsigned got = fetch_rays(F, !has, n, next, lane);
-            if (!has && got != 0xFFFFFFFFu) {
-                idx = got;
-                float4 o = sh_o[idx], d = sh_d[idx];
+            unsigned got = fetch_rays(F, !C.has && c == 0u, n, next, lane);
+            got = __shfl_sync(kFull, got, gl);
+            if (!C.has && got != 0xFFFFFFFFu) {
+                const float4 o = sh_o[got], d = sh_d[got];
                 r = make_ray(xyz(o), xyz(d));
-                dist = o.w;
                 const uint32_t tag = __float_as_uint(d.w);
                 const int phase = (tag & 0x80000000u) ? 1 : 2;
                 slot = tag & 0x7FFFFFFFu;
-                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
-                    vis[slot] = binary_visible<COUNT>(S, r, dist, phase, &st) ? 1 : 0;
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                    if (c == 0u) vis[slot] = binary_visible<COUNT>(S, r, o.w, phase, &st) ? 1 : 0;
                 } else {
-                    shadow4_begin(T, r, dist, phase);
-                    has = true;
+                    coop_shadow_begin(C, o.w, phase);
                 }
             }
             exhausted = F.dry && F.lo >= F.hi;
         }
-        unsigned act = __ballot_sync(0xffffffffu, has);
+        unsigned act = __ballot_sync(kFull, C.has);
         if (!act) {
             if (exhausted) break;
             continue;
         }
         do {
-            if (has && !shadow4_step<COUNT>(S, r, dist, T, &st)) {
-                vis[slot] = T.visible ? 1 : 0;
-                has = false;
-            }
-            act = __ballot_sync(0xffffffffu, has);
-        } while (act && (exhausted || __popc(act) > kRefillBelow));
+            const int res = coop_shadow_step<COUNT>(S, r, C, stk, &st);
+            if (res && c == 0u) vis[slot] = res == 1 ? 1 : 0;
+            act = __ballot_sync(kFull, C.has);
+        } while (act && (exhausted || __popc(act) > 4 * B2PT_COOP_REFILL));
     }
     if (COUNT) {
         unsigned long long nodes = warp_sum((unsigned long long)st.nodes), prims = warp_sum((unsigned long long)st.prims);
@@ -985,29 +1253,28 @@ __device__ __forceinline__ void st3(float *p, long long i, f3 v) { p[3 * i] = v.
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;          \
     if (i >= (n)) return;
 
-template <bool COUNT>
-__global__ void k_intersect(SceneView S, const float *o, const float *d, long long n, int *prim, double *t, Counters *cnt) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long nodes = 0, prims = 0;
-    if (i < n) {
-        TravStats st{0, 0};
-        Hit h = closest_hit4<COUNT>(S, make_ray(ld3(o, i), ld3(d, i)), &st);
-        prim[i] = h.prim; t[i] = h.t;
-        nodes = st.nodes; prims = st.prims;
-    }
-    if (COUNT) {
-        nodes = warp_sum(nodes); prims = warp_sum(prims);
-        if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
-    }
+// Scene::intersect for the parity entry point: the rays are packed into a queue and walked by the EXTEND KERNEL itself, so the
+// bit-exactness tests (hit id + t as u64 bits) exercise the code path of the render, not a sibling of it.
+__global__ void k_pack_rays(const float *o, const float *d, unsigned n, float4 *qo, float4 *qd, uint32_t *qinfo, unsigned *n_dev, unsigned *cursor) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { *n_dev = n; *cursor = 0; }
+    if (i >= n) return;
+    qo[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], 0.f);
+    qd[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], 0.f);
+    qinfo[i] = 1u << INFO_MASK_SHIFT;
 }
-__global__ void k_shadow(SceneView S, const float *o, const float *d, const float *dist, long long n, int *visible) {
-    BATCH_INDEX(n)
-    TravStats st{0, 0};
-    #if B2PT_SHADOW_WIDE
-    visible[i] = light_visible4<false>(S, make_ray(ld3(o, i), ld3(d, i)), dist[i], &st) ? 1 : 0;
-#else
-    visible[i] = light_visible<false>(S, make_ray(ld3(o, i), ld3(d, i)), dist[i], &st) ? 1 : 0;
-#endif
+// The visibility decision for the parity entry point, through the SHADOW KERNEL itself: every ray starts with the window search
+// by traversal (phase 1; the render answers it from the light neighbourhood table first).
+__global__ void k_pack_shadow(const float *o, const float *d, const float *dist, unsigned n, float4 *sh_o, float4 *sh_d, unsigned *n_dev, unsigned *cursor) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { *n_dev = n; *cursor = 0; }
+    if (i >= n) return;
+    sh_o[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], dist[i]);
+    sh_d[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], __uint_as_float(i | 0x80000000u));
+}
+__global__ void k_vis_to_int(const unsigned char *vis, unsigned n, int *out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = vis[i];
 }
 __global__ void k_tri(const float *v9, const float *o, const float *d, long long n, int *hit, double *t) {
     BATCH_INDEX(n)
@@ -1611,9 +1878,8 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_entries, const float4 *, 19, packed.lt_entries.data(), 16 * packed.lt_entries.size());
     UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
-    UP(leaf, const float4 *, 22, packed.leaf.data(), 16 * packed.leaf.size());
-    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.rows.data(), sizeof(float) * packed.quads.rows.size());
-    v.quad_o_max = packed.quads.o_max;
+    UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
+    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.nodes.data(), sizeof(b2pt_node) * packed.quads.nodes.size());
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;
@@ -1828,17 +2094,23 @@ int b2pt_render_samples(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render
 
 int b2pt_intersect_batch(b2pt_ctx *ctx, const float *origins, const float *dirs, int64_t n, int32_t *prim_id, double *t, b2pt_stats *stats) {
     NEED_SCENE()
-    if (n < 0 || !origins || !dirs || !prim_id || !t) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    if (n < 0 || n > 0x7FFFFFFF || !origins || !dirs || !prim_id || !t) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
     Scratch s(ctx);
     const float *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n);
     int *dp = s.out<int>(n);
     double *dt = s.out<double>(n);
+    float4 *qo = s.out<float4>(n), *qd = s.out<float4>(n);
+    uint32_t *qinfo = s.out<uint32_t>(n);
+    float *tf = s.out<float>(n);
+    unsigned *ctl = s.out<unsigned>(4);
     if (s.err) return s.finish("intersect_batch");
     CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), ctx->stream));
+    if (n) k_pack_rays<<<nblocks(n), 256, 0, ctx->stream>>>(o, d, (unsigned)n, qo, qd, qinfo, ctl, ctl + 1);
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (n) {
-        if (stats) k_intersect<true><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, o, d, n, dp, dt, ctx->d_cnt);
-        else k_intersect<false><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, o, d, n, dp, dt, ctx->d_cnt);
+        const unsigned g = grid_for((size_t)n, ctx, 16);
+        if (stats) extend_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->view, qo, qd, qinfo, ctl, ctl + 1, dp, tf, ctx->d_cnt, dt);
+        else extend_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->view, qo, qd, qinfo, ctl, ctl + 1, dp, tf, ctx->d_cnt, dt);
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     s.back(prim_id, dp, n); s.back(t, dt, n);
@@ -1849,7 +2121,7 @@ int b2pt_intersect_batch(b2pt_ctx *ctx, const float *origins, const float *dirs,
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
         stats->gpu_ms = stats->extend_ms = ms;
-        stats->kernel_launches = stats->extend_launches = n ? 1 : 0;
+        stats->kernel_launches = n ? 2 : 0; stats->extend_launches = n ? 1 : 0;
         stats->rays_traced_closest = stats->rays_reference = (uint64_t)n;
         stats->nodes_fetched = stats->extend_nodes = ctx->h_cnt->nodes; stats->prims_tested = stats->extend_prims = ctx->h_cnt->prims;
     }
@@ -1858,14 +2130,21 @@ int b2pt_intersect_batch(b2pt_ctx *ctx, const float *origins, const float *dirs,
 
 int b2pt_shadow_batch(b2pt_ctx *ctx, const float *origins, const float *dirs, const float *dist, int64_t n, int32_t *visible, b2pt_stats *stats) {
     NEED_SCENE()
-    if (n < 0 || !origins || !dirs || !dist || !visible) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
+    if (n < 0 || n >= 0x7FFFFFFF || !origins || !dirs || !dist || !visible) return fail(ctx, B2PT_ERR_INVALID, "bad arguments");
     Scratch s(ctx);
     const float *o = s.in(origins, 3 * n), *d = s.in(dirs, 3 * n), *ds = s.in(dist, n);
     int *dv = s.out<int>(n);
+    float4 *so = s.out<float4>(n), *sd = s.out<float4>(n);
+    unsigned char *vis = s.out<unsigned char>(n + 16);
+    unsigned *ctl = s.out<unsigned>(4);
     if (s.err) return s.finish("shadow_batch");
-    if (n) k_shadow<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->view, o, d, ds, n, dv);
+    if (n) {
+        k_pack_shadow<<<nblocks(n), 256, 0, ctx->stream>>>(o, d, ds, (unsigned)n, so, sd, ctl, ctl + 1);
+        shadow_kernel<false><<<grid_for((size_t)n, ctx, 16), kBlock, 0, ctx->stream>>>(ctx->view, so, sd, ctl, ctl + 1, vis, ctx->d_cnt);
+        k_vis_to_int<<<nblocks(n), 256, 0, ctx->stream>>>(vis, (unsigned)n, dv);
+    }
     s.back(visible, dv, n);
-    if (stats) { std::memset(stats, 0, sizeof *stats); stats->rays_traced_shadow = (uint64_t)n; stats->kernel_launches = stats->shadow_launches = n ? 1 : 0; }
+    if (stats) { std::memset(stats, 0, sizeof *stats); stats->rays_traced_shadow = (uint64_t)n; stats->kernel_launches = n ? 3 : 0; stats->shadow_launches = n ? 1 : 0; }
     return s.finish("shadow_batch");
 }
 

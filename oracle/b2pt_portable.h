@@ -50,9 +50,12 @@ static inline uint32_t b2pt_stream_word(uint32_t seed_lo, uint32_t seed_hi, uint
     b2pt_philox4x32_10(ctr, key, out);
     return out[dim & 3u];
 }
-/* 24-bit uniform in [0,1): what libstdc++'s uniform_real_distribution<float>
- * returns for a 32-bit engine word whose low 8 bits are clear. */
-static inline float b2pt_u01(uint32_t word) { return (float)(word >> 8) * 5.9604644775390625e-08f; }
+/* The uniform libstdc++'s uniform_real_distribution<float>(0,1) returns for a 32-bit engine word (generate_canonical<float, 24>):
+ * float(word) / 2^32 with the int-to-float conversion's round-to-nearest, nextafter(1, 0) when that reaches 1. */
+static inline float b2pt_u01(uint32_t word) {
+    float u = (float)word * 2.3283064365386963e-10f;
+    return u < 1.f ? u : 0.99999994f;
+}
 
 /* ---- portable sin/cos ------------------------------------------------------
  * double-precision evaluation, Cody-Waite reduction by pi/2 and the fdlibm

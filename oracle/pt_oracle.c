@@ -604,6 +604,7 @@ void pto_render_frame(const pto_scene *s, const b2pt_camera *cam, int sample_beg
 }
 /* The oracle's own Philox (b2pt_portable.h, written independently of csrc/pt_math.cuh): raw block, and the uniforms of a sample
  * stream as the paths consume them. */
+float pto_u01(uint32_t word) { return b2pt_u01(word); }
 void pto_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { b2pt_philox4x32_10(ctr, key, out); }
 void pto_stream_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t tag, uint32_t dim_begin, int count, float *out) {
     for (int i = 0; i < count; ++i)

@@ -34,6 +34,7 @@ void pto_render_samples_counted(const pto_scene *s, const b2pt_camera *cam, cons
                                 uint64_t seed, float *out, unsigned long long *rays, unsigned long long *vertices);
 void pto_render_frame(const pto_scene *s, const b2pt_camera *cam, int sample_begin, int sample_count, int spp_total, uint64_t seed, float *fb);
 /* Philox4x32-10 of b2pt_portable.h: one block, and draws dim_begin.. of the stream (pixel, sample, tag) as uniforms */
+float pto_u01(uint32_t word);  /* the uniform of an engine word */
 void pto_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void pto_stream_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t tag, uint32_t dim_begin, int count, float *out);
 /* Scene::castRay (src/Scene.cpp:85-184) on explicit rays with scripted uniforms */

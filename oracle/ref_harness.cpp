@@ -30,7 +30,7 @@
 #include "b2pt_portable.h"
 
 // ---- engine back-end ---------------------------------------------------------
-enum { RNG_MT = 0, RNG_SCRIPT = 1, RNG_PHILOX = 2 };
+enum { RNG_MT = 0, RNG_SCRIPT = 1, RNG_PHILOX = 2, RNG_WORD = 3 };
 struct RngCtx {
     int mode = RNG_MT;
     std::b2pt_real_mt19937 mt{5489u};
@@ -40,9 +40,11 @@ struct RngCtx {
     uint32_t seed_lo = 0, seed_hi = 0, pixel = 0, sample = 0, tag = 0, dim = 0;
     uint32_t cached_block = 0xFFFFFFFFu, cached_tag = 0xFFFFFFFFu, words[4];
     unsigned long long draws = 0;
+    uint32_t free_ctr = 0;
 };
 static thread_local RngCtx g_rng;
 static uint32_t g_mt_seed = 20251018u;
+static int g_free_engine = 0;  // 0: std::mt19937 (the reference's engine), 1: Philox words in sequence (diagnostic)
 
 extern "C" uint32_t b2pt_oracle_next_u32() {
     RngCtx &c = g_rng;
@@ -53,6 +55,8 @@ extern "C" uint32_t b2pt_oracle_next_u32() {
         float u = c.script[c.script_i++];
         return ((uint32_t)(u * 16777216.0f)) << 8;
     }
+    case RNG_WORD:
+        return c.seed_lo;
     case RNG_PHILOX: {
         uint32_t blk = c.dim >> 2;
         if (blk != c.cached_block || c.tag != c.cached_tag) {
@@ -62,9 +66,14 @@ extern "C" uint32_t b2pt_oracle_next_u32() {
         }
         uint32_t w = c.words[c.dim & 3u];
         c.dim++;
-        return w & 0xFFFFFF00u;
+        return w;  // the full word, like the reference's own engine hands to uniform_real_distribution
     }
     default:
+        if (g_free_engine == 1) {  // diagnostic: a free-running stream of Philox words (one sequence per thread) instead of mt19937
+            uint32_t ctr[4] = {c.free_ctr >> 2, 0x5EEDu, (uint32_t)omp_get_thread_num(), 0xF4EEu}, key[2] = {g_mt_seed, 0x12345u}, out[4];
+            b2pt_philox4x32_10(ctr, key, out);
+            return out[c.free_ctr++ & 3u];
+        }
         if (!c.mt_seeded) {  // one decorrelated free-running stream per OpenMP thread
             c.mt.seed(0x9E3779B9u * (uint32_t)(omp_get_thread_num() + 1) + g_mt_seed);
             c.mt_seeded = true;
@@ -350,6 +359,13 @@ float ref_uniform_from_script(float u) {
     g_rng.mode = RNG_MT;
     return r;
 }
+// the uniform get_random_float() (global.hpp:42-53: uniform_real_distribution<float> on the engine) returns for a given engine word
+float ref_uniform_from_word(uint32_t w) {
+    g_rng.mode = RNG_WORD; g_rng.seed_lo = w;
+    float r = get_random_float();
+    g_rng.mode = RNG_MT;
+    return r;
+}
 // ---- (a3) Scene::castRay on explicit rays, scripted uniforms per ray -------------------------
 // script: n rows of `stride` uniforms; returns radiance and how many uniforms were consumed.
 void ref_cast_ray_scripted(void *h, const float *o, const float *d, const int *wl, const float *script, int stride,
@@ -442,6 +458,53 @@ void ref_render_samples_philox(void *h, const int *pixels, int npix, int sample_
     }
     if (draws) *draws = total;
 }
+void ref_set_free_engine(int e, uint32_t seed) { g_free_engine = e; g_mt_seed = seed; }
+// Per-sample values of listed pixels on the reference's own sampling scheme (free-running mt19937, independent draws for the
+// three castRay calls): out[(q*sample_count + k)*3 + c].
+void ref_render_samples_free(void *h, const int *pixels, int npix, int sample_count, uint32_t seed, int threads, float *out) {
+    RefScene *S = (RefScene *)h;
+    CamSetup c = cam_setup(S->scene);
+    if (threads <= 0) threads = 8;
+#pragma omp parallel num_threads(threads)
+    {
+        g_rng.mode = RNG_MT;
+        g_rng.mt.seed(0x9E3779B9u * (uint32_t)(omp_get_thread_num() + 1) + seed);
+        g_rng.mt_seeded = true;
+#pragma omp for schedule(static, 8)
+        for (int q = 0; q < npix; ++q) {
+            int m = pixels[q];
+            for (int k = 0; k < sample_count; ++k) {
+                Vector3f pos, dir;
+                camera_ray(c, m % c.cam.width, m / c.cam.width, pos, dir);
+                for (int ch = 0; ch < 3; ++ch)
+                    out[((size_t)q * sample_count + k) * 3 + ch] = S->scene.castRay(Ray(pos, dir), 0, WL[ch]);
+            }
+        }
+    }
+}
+// Diagnostic twin of ref_render_samples_philox: the three wavelength paths read THREE different keyed streams (tags 0, 2, 3)
+// instead of the same one.  Used by tests/test_statistical.py to separate "keyed streams" from "streams shared by R, G, B".
+void ref_render_samples_philox_split(void *h, const int *pixels, int npix, int sample_begin, int sample_count,
+                                     uint32_t seed_lo, uint32_t seed_hi, float *out) {
+    RefScene *S = (RefScene *)h;
+    CamSetup c = cam_setup(S->scene);
+    static const uint32_t TAG[3] = {B2PT_STREAM_PATH, 2u, 3u};
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int q = 0; q < npix; ++q) {
+        int m = pixels[q];
+        for (int k = 0; k < sample_count; ++k) {
+            uint32_t s = (uint32_t)(sample_begin + k);
+            rng_philox(seed_lo, seed_hi, (uint32_t)m, s, B2PT_STREAM_CAMERA);
+            Vector3f pos, dir;
+            camera_ray(c, m % c.cam.width, m / c.cam.width, pos, dir);
+            for (int ch = 0; ch < 3; ++ch) {
+                rng_philox(seed_lo, seed_hi, (uint32_t)m, s, TAG[ch]);
+                out[((size_t)q * sample_count + k) * 3 + ch] = S->scene.castRay(Ray(pos, dir), 0, WL[ch]);
+            }
+        }
+        g_rng.mode = RNG_MT;
+    }
+}
 // Whole frame, accumulated exactly like Renderer.cpp:80 (fb[m] += rgb / spp_total, sample order).
 void ref_render_frame_philox(void *h, int sample_begin, int sample_count, int spp_total, uint32_t seed_lo,
                              uint32_t seed_hi, int threads, float *fb) {
@@ -483,7 +546,7 @@ void ref_render_frame_free(void *h, int spp, uint32_t seed, int threads, float *
         g_rng.mode = RNG_MT;
         g_rng.mt.seed(0x9E3779B9u * (uint32_t)(omp_get_thread_num() + 1) + seed);
         g_rng.mt_seeded = true;
-#pragma omp for schedule(dynamic, 8)
+#pragma omp for schedule(static, 8)  // static: which thread (engine) renders which pixel does not depend on timing, so the frame is reproducible
         for (int m = 0; m < W * H; ++m) {
             double sum[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
             for (int k = 0; k < spp; ++k) {

@@ -96,6 +96,11 @@ def ref_lib():
         L.ref_render_frame_philox.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, b2pt.c_float_p]
         L.ref_render_real.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         L.ref_render_frame_free.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, b2pt.c_float_p, b2pt.c_float_p]
+        L.ref_render_samples_free.argtypes = [C.c_void_p, b2pt.c_int_p, C.c_int, C.c_int, C.c_uint32, C.c_int, b2pt.c_float_p]
+        L.ref_render_samples_philox_split.argtypes = [C.c_void_p, b2pt.c_int_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, b2pt.c_float_p]
+        L.ref_set_free_engine.argtypes = [C.c_int, C.c_uint32]
+        L.ref_uniform_from_word.argtypes = [C.c_uint32]
+        L.ref_uniform_from_word.restype = C.c_float
         _ref = L
     return _ref
 
@@ -261,6 +266,13 @@ class Ref:
         self.L.ref_render_frame_free(self.h, spp, seed & 0xFFFFFFFF, threads, fp(mean), fp(m2))
         var = np.maximum(m2.astype(np.float64) - mean.astype(np.float64) ** 2, 0.0)
         return mean, var
+
+    def render_samples_free(self, pixels, sample_count, seed=1, threads=0):
+        """Per-sample values [pixels, sample_count, 3] on the reference's own sampling scheme (free-running mt19937 per thread)."""
+        px = i32(pixels)
+        out = np.zeros((len(px), sample_count, 3), np.float32)
+        self.L.ref_render_samples_free(self.h, ip(px), len(px), sample_count, seed & 0xFFFFFFFF, threads, fp(out))
+        return out
 
     def render_frame(self, sample_begin, sample_count, spp_total, seed=SEED, threads=0, fb=None):
         cam = self.scene.camera

@@ -294,12 +294,29 @@ def test_camera_rays_bit_exact(world):
 
 
 def test_uniform_mapping():
-    """(word >> 8) * 2^-24 is what libstdc++'s uniform_real_distribution<float> yields for the hooked engine."""
+    """pt::unit_from_word and the oracle's b2pt_u01 are what libstdc++'s uniform_real_distribution<float> (through the reference's own
+    get_random_float, global.hpp:42-53) yields for an engine word — the FULL 32-bit word, round to nearest, never 1."""
+    import ctypes as C
     u = S.hc_stream_uniforms(S.SEED, 99, 7, 0, 0, 64)
     assert (u >= 0).all() and (u < 1).all()
-    lib = S.ref_lib()
-    for x in u[:32]:
-        assert lib.ref_uniform_from_script(float(x)) == np.float32(x)
+    lib, hc, pto = S.ref_lib(), S.hc_lib(), S.pto_lib()
+    lib.ref_uniform_from_word.restype = C.c_float
+    lib.ref_uniform_from_word.argtypes = [C.c_uint32]
+    hc.hc_u01.restype = C.c_float
+    hc.hc_u01.argtypes = [C.c_uint32]
+    pto.pto_u01.restype = C.c_float
+    pto.pto_u01.argtypes = [C.c_uint32]
+    words = [0, 1, 255, 256, 0x7FFFFFFF, 0x80000000, 0xFFFFFF00, 0xFFFFFF7F, 0xFFFFFF80, 0xFFFFFFFF, 0x00FFFFFF, 0x01000001, 0x3FFFFFE0, 0x3FFFFFF0]
+    words += [int(x) for x in np.random.RandomState(5).randint(0, 2 ** 32, 4000, dtype=np.uint64)]
+    for w in words:
+        want = lib.ref_uniform_from_word(w)
+        assert hc.hc_u01(w) == want and pto.pto_u01(w) == want, hex(w)
+        assert 0.0 <= want < 1.0
+    assert lib.ref_uniform_from_word(0xFFFFFFFF) == np.float32(0.99999994)
+    # uniforms below 1/2 keep mantissa bits a 24-bit truncation would zero
+    small = S.hc_stream_uniforms(S.SEED, 3, 1, 0, 0, 4096)
+    small = small[(small < 0.25) & (small > 0)]
+    assert (np.frombuffer(small.tobytes(), np.uint32) & 1).mean() > 0.3
     # streams are functions of (seed, pixel, sample, tag, dim) only
     assert np.array_equal(S.hc_stream_uniforms(S.SEED, 99, 7, 0, 5, 10), u[5:15])
     assert not np.array_equal(S.hc_stream_uniforms(S.SEED, 99, 8, 0, 0, 64), u)

@@ -4,9 +4,17 @@ The reference draws every uniform from a free-running mt19937 per OpenMP thread 
 sample (src/Renderer.cpp:77-79) consume independent draws.  The CUDA path — and the oracle replay every other parity
 test compares it with — keys a Philox stream by (pixel, sample) and lets R, G and B read the SAME stream, which is what
 allows one ray to carry three wavelength paths.  Per-channel expectations are unchanged by that; this file is the test
-that would catch it if they were not: frames of the keyed / shared scheme against `ref_render_frame_free`
-(oracle/ref_harness.cpp), the reference's pixel loop on free-running engines, with per-pixel 99 % confidence intervals
-built from the per-sample variances of both sides, the frame mean per channel, and RMSE against the expected noise.
+that would catch it if they were not: per-sample values of the keyed / shared scheme against `ref_render_samples_free`
+(oracle/ref_harness.cpp), the reference's pixel loop on free-running engines, through
+
+* per-pixel 99 % confidence intervals built from the per-sample variances of both sides,
+* the frame mean per channel and the RMSE against the expected noise,
+* the DISTRIBUTION of the per-sample values (bin fractions with binomial intervals).
+
+The last one is the sharp one.  The reference's visibility test |t - dist| < EPSILON sits below float resolution at scene
+scale, so its acceptance rate depends on the low mantissa bits of the uniforms: streams that truncated the engine word to
+24 bits (round 1) rendered the Cornell box 1 % brighter than the reference, 10 sigma in the (0.5, 1] bin while the frame mean
+was only 3 sigma off.  The streams now convert the full 32-bit word exactly as libstdc++ does (pt::unit_from_word).
 
 * `-m "not gpu"`: the oracle's own replay of the keyed scheme vs the free-running one (the scheme itself).
 * `-m gpu`: the CUDA path through the C ABI vs the free-running reference (scheme + kernels + every exact shortcut:
@@ -22,39 +30,48 @@ b2pt = S.b2pt
 pytestmark = pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref/libref_oracle.so not built")
 
 Z99 = 2.576
+BINS = [-np.inf, -1e-9, 1e-9, 0.05, 0.2, 0.5, 1.0, 2.0, 5.0, np.inf]
 
 
-def compare(samples_keyed, n_keyed, free_mean, free_var, n_free):
-    """samples_keyed: [pixels, n_keyed, 3] per-sample values of the keyed scheme; free_*: [pixels, 3]."""
-    sm = samples_keyed.astype(np.float64)
-    mean_k, var_k = sm.mean(1), sm.var(1)
-    d = mean_k - free_mean
-    se = np.sqrt(var_k / n_keyed + free_var / n_free)
+def compare(keyed, free):
+    """keyed, free: per-sample values [pixels, n, 3] of the two schemes."""
+    k, f = keyed.astype(np.float64), free.astype(np.float64)
+    n_k, n_f = k.shape[1], f.shape[1]
+    mean_k, var_k, mean_f, var_f = k.mean(1), k.var(1), f.mean(1), f.var(1)
+    d = mean_k - mean_f
+    se = np.sqrt(var_k / n_k + var_f / n_f)
     # float rounding floor: pixels that are deterministic on both sides (black, saturated, pure sky) differ by rounding only
-    tol = Z99 * se + 2e-5 + 2e-4 * np.maximum(np.abs(mean_k), np.abs(free_mean))
-    inside = np.abs(d) <= tol
-    z = np.abs(d) / (se + 1e-5 + 1e-4 * np.maximum(np.abs(mean_k), np.abs(free_mean)))
-    n_pix = d.shape[0]
-    se_mean = np.sqrt((se ** 2).sum(0)) / n_pix
+    floor = 2e-5 + 2e-4 * np.maximum(np.abs(mean_k), np.abs(mean_f))
+    inside = np.abs(d) <= Z99 * se + floor
+    z = np.abs(d) / (se + floor)
+    se_mean = np.sqrt((se ** 2).sum(0)) / d.shape[0]
+    # distribution of the per-sample values, all channels pooled per bin
+    worst = 0.0
+    for a, b in zip(BINS[:-1], BINS[1:]):
+        fk, ff = ((k > a) & (k <= b)).mean(), ((f > a) & (f <= b)).mean()
+        p = 0.5 * (fk + ff)
+        sig = np.sqrt(max(p * (1 - p), 1e-12) * (1.0 / k.size + 1.0 / f.size))
+        worst = max(worst, abs(fk - ff) / (sig + 2e-5))
     return {"inside": float(inside.mean()), "far": float((z > 6.0).mean()), "mean_diff": d.mean(0), "se_mean": se_mean,
-            "rmse": float(np.sqrt((d ** 2).mean())), "noise": float(np.sqrt((se ** 2).mean())), "mean": float(free_mean.mean())}
+            "rmse": float(np.sqrt((d ** 2).mean())), "noise": float(np.sqrt((se ** 2).mean())), "mean": float(mean_f.mean()), "worst_bin_sigma": float(worst)}
 
 
 def assert_equivalent(r, what):
     assert r["inside"] >= 0.98, (what, r)          # 99 % intervals: 0.99 expected
     assert r["far"] <= 1e-3, (what, r)             # nothing systematic hiding in a few pixels
-    assert (np.abs(r["mean_diff"]) <= 4.0 * r["se_mean"] + 1e-5).all(), (what, r)  # no bias in any channel
+    assert (np.abs(r["mean_diff"]) <= 4.5 * r["se_mean"] + 1e-5).all(), (what, r)  # no bias in any channel
     assert r["rmse"] <= 1.5 * r["noise"] + 1e-6, (what, r)
+    assert r["worst_bin_sigma"] <= 5.0, (what, r)  # the two schemes draw per-sample values from the same distribution
     assert r["mean"] > 0.01, (what, r)
 
 
 CASES = {
     # name: (scene factory, keyed spp, free-running spp)
-    "cornell": (lambda: scenes.cornell(48, 48), 192, 192),
+    "cornell": (lambda: scenes.cornell(48, 48), 384, 384),
     "chess_sky_dof": (lambda: scenes.chess(128, 72, dof=True, sky=True), 96, 96),
 }
 GPU_CASES = {
-    "cornell": (lambda: scenes.cornell(96, 96), 256, 128),
+    "cornell": (lambda: scenes.cornell(96, 96), 512, 192),
     "chess_sky_dof": (lambda: scenes.chess(160, 90, dof=True, sky=True), 256, 96),
     "chess_dark_nee32": (lambda: scenes.chess(160, 90, dof=False, sky=False, n_dir=32), 128, 48),
 }
@@ -67,9 +84,7 @@ def test_keyed_shared_streams_match_the_free_running_reference(which):
     ref = S.Ref(sc, env)
     cam = sc.camera
     px = np.arange(cam.width * cam.height, dtype=np.int32)
-    keyed = ref.render_samples(px, 0, n_k)
-    mean_f, var_f = ref.render_free(n_f, seed=7)
-    r = compare(keyed, n_k, mean_f.reshape(-1, 3).astype(np.float64), var_f.reshape(-1, 3), n_f)
+    r = compare(ref.render_samples(px, 0, n_k), ref.render_samples_free(px, n_f, seed=7))
     assert_equivalent(r, which)
     ref.close()
     sc.close()
@@ -89,8 +104,7 @@ def test_gpu_frame_matches_the_free_running_reference(which):
     # the frame entry point accumulates the same samples: per-sample output and frame agree
     fb, _ = ctx.render(cam, n_g)
     assert np.allclose(fb.reshape(-1, 3), got.astype(np.float64).mean(1), rtol=2e-4, atol=2e-5)
-    mean_f, var_f = ref.render_free(n_f, seed=11)
-    r = compare(got, n_g, mean_f.reshape(-1, 3).astype(np.float64), var_f.reshape(-1, 3), n_f)
+    r = compare(got, ref.render_samples_free(px, n_f, seed=11))
     assert_equivalent(r, which)
     ctx.close()
     ref.close()
