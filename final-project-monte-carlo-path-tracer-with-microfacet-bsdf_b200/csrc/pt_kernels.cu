@@ -271,10 +271,10 @@ __device__ __forceinline__ unsigned fetch_rays(Fetch &F, bool idle, unsigned n, 
 }
 
 #ifndef B2PT_TRAV_MIN_BLOCKS
-#define B2PT_TRAV_MIN_BLOCKS 9  // shadow kernel: 56 registers / 9 blocks per SM (measured: 10 blocks -1.5 %, 8 -0.8 %, 12 -4 %)
+#define B2PT_TRAV_MIN_BLOCKS 8  // shadow kernel: 64 registers / 8 blocks per SM (r02c: 8 blocks +1-3 % over 9 with its 56 registers and spills)
 #endif
 #ifndef B2PT_EXT_MIN_BLOCKS
-#define B2PT_EXT_MIN_BLOCKS 9  // the four-wide walk keeps four entry distances and four child indices live: 56 registers / 9 blocks (measured: 8 blocks -0.6 %, 10 -3.5 %)
+#define B2PT_EXT_MIN_BLOCKS 8  // the four-wide walk keeps four entry distances and four child indices live: 64 registers / 8 blocks (r02c: +2-3 % over 9 blocks / 56 registers, which spilled)
 #endif
 // Rays whose slab products can be NaN (pt::ray_needs_reference_tree) — and every ray of a scene whose four-wide tree was not
 // built — take the whole binary walk out of line; they are rare, the call keeps the main loop's registers for the quad walk.
@@ -290,184 +290,6 @@ __device__ __noinline__ bool binary_visible(const SceneView &S, const Ray &r, fl
     return T.visible;
 }
 
-// ---- four lanes per ray ------------------------------------------------------------------------------------------------
-// ncu (profiles/r01q, r02b) shows the one-lane-per-ray walk bound by the L1 data pipe, not by arithmetic: every lane reads its
-// own 128-byte quad with eight 16-byte loads, i.e. eight L1 wavefronts per lane and step, and halving the box arithmetic
-// (profiles/r02c) changed nothing.  Here a ray is walked by FOUR adjacent lanes, one per child of the quad: lane c loads the
-// 32 bytes of child c (the group's four loads fall into one 128-byte line: two wavefronts per ray and step instead of eight),
-// tests that one box with the reference's arithmetic, tests its own primitive when the child is a leaf whose box passed, and
-// the group agrees on the next quad with two butterfly shuffles.  Children that are not taken are pushed by the lane that
-// owns them onto ITS OWN stack together with their depth; the group pops the deepest pending entry (ties: the nearest), which
-// keeps the depth-first discipline and therefore the stack bound.  The order in which candidates are met differs from the
-// one-lane walk, the set of primitives tested per ray (own leaf box passed, entry not beyond the best hit) and the tie rule
-// (larger primitive id) do not: hits and t are bit-identical (tests/test_gpu_parity.py through b2pt_intersect_batch).
-#ifndef B2PT_COOP
-#define B2PT_COOP 1
-#endif
-#ifndef B2PT_COOP_REFILL
-#define B2PT_COOP_REFILL 5  // new rays are fetched when at most this many of the warp's eight groups are still walking
-#endif
-constexpr unsigned kFull = 0xffffffffu;
-__device__ __forceinline__ uint32_t nonneg_bits(float t) { return __float_as_uint(fmaxf(t, 0.f)); }  // order-preserving for t >= 0
-struct Coop {
-    Hit h;           // best hit so far (identical in the four lanes)
-    float bound;
-    uint32_t quad;   // the quad the group is at
-    int level;       // its depth
-    int sp;          // entries on THIS lane's stack
-    bool has;        // the group is walking a ray
-};
-__device__ __forceinline__ void coop_begin(Coop &C) {
-    C.h.t = 1.7976931348623157e308;
-    C.h.prim = -1;
-    C.bound = INFINITY;
-    C.quad = 0; C.level = 0; C.sp = 0;
-    C.has = true;
-}
-// One step of every walking group of the warp.  Returns (per lane) true when the lane's group has just finished its ray: C.h is
-// the result.  All 32 lanes must call.
-template <bool COUNT>
-__device__ __forceinline__ bool coop_step(const SceneView &S, const Ray &r, Coop &C, uint2 *stk, TravStats *st) {
-    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
-    // my child of the group's quad
-    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-    if (C.has) {
-        const float4 *p = S.nodes4 + 8 * (size_t)C.quad + 2 * c;
-        lo = PT_LDG4(p); hi = PT_LDG4(p + 1);
-    }
-    float t = 0.f;
-    const bool hit = C.has && box_hit(xyz(lo), xyz(hi), r, &t) && !(t > C.bound);
-    const uint32_t a = f2u(lo.w);
-    const unsigned meta = __shfl_sync(kFull, f2u(hi.w), gl) >> 8;  // slot 0 carries the quad's leaf mask (bits 0-3) and sphere mask (4-7)
-    const unsigned ghit = (__ballot_sync(kFull, hit) >> gl) & 15u;
-    const bool is_leaf = (meta >> c) & 1u;
-    if (COUNT && C.has) st->nodes += 1;
-    // leaf children whose box passed: each lane tests its own primitive, the group keeps the closest (ties: larger id)
-    if (__any_sync(kFull, (ghit & meta & 15u) != 0u)) {
-        double tt = 1.7976931348623157e308;
-        int pr = -1;
-        if (hit && is_leaf) {
-            double t2;
-            if (COUNT) st->prims++;
-            if (prim_hit(S, a, ((meta >> (4 + c)) & 1u) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t2)) { tt = t2; pr = (int)a; }
-        }
-#pragma unroll
-        for (int off = 1; off <= 2; off <<= 1) {
-            const double ot = __shfl_xor_sync(kFull, tt, off);
-            const int op = __shfl_xor_sync(kFull, pr, off);
-            if (ot < tt || (ot == tt && op > pr)) { tt = ot; pr = op; }
-        }
-        if (pr >= 0 && (tt < C.h.t || (tt == C.h.t && pr > C.h.prim))) { C.h.t = tt; C.h.prim = pr; C.bound = prune_bound(tt); }
-    }
-    // interior children still wanted: the group goes to the nearest, the others are pushed by their lanes
-    const bool cand = hit && !is_leaf && !(t > C.bound);
-    const uint32_t key = cand ? ((nonneg_bits(t) & ~3u) | c) : 0xFFFFFFFFu;
-    uint32_t kmin = min(key, __shfl_xor_sync(kFull, key, 1));
-    kmin = min(kmin, __shfl_xor_sync(kFull, kmin, 2));
-    const uint32_t a_next = __shfl_sync(kFull, a, gl + (kmin & 3u));
-    const bool descend = kmin != 0xFFFFFFFFu;
-    if (descend) {
-        if (cand && c != (kmin & 3u)) stk[C.sp++] = make_uint2(a | ((uint32_t)(C.level + 1) << 24), f2u(t));
-        C.quad = a_next;
-        C.level++;
-    }
-    // nothing wanted here: pop the deepest pending entry of the group (its lanes first drop what the bound has overtaken)
-    const bool need_pop = C.has && !descend;
-    bool finished = false;
-    if (__any_sync(kFull, need_pop)) {
-        uint32_t pk = 0, ex = 0;
-        if (need_pop) {
-            while (C.sp > 0 && u2f(stk[C.sp - 1].y) > C.bound) --C.sp;
-            if (C.sp > 0) {
-                const uint2 e = stk[C.sp - 1];
-                ex = e.x;
-                pk = ((e.x >> 24) << 26) | ((0xFFFFFFu - (nonneg_bits(u2f(e.y)) >> 8)) << 2) | (3u - c);
-            }
-        }
-        uint32_t pmax = max(pk, __shfl_xor_sync(kFull, pk, 1));
-        pmax = max(pmax, __shfl_xor_sync(kFull, pmax, 2));
-        const unsigned winner = 3u - (pmax & 3u);
-        const uint32_t wx = __shfl_sync(kFull, ex, gl + winner);
-        if (need_pop) {
-            if (pmax == 0u) {
-                C.has = false;
-                finished = true;
-            } else {
-                if (c == winner) --C.sp;
-                C.quad = wx & 0xFFFFFFu;
-                C.level = (int)(wx >> 24);
-            }
-        }
-    }
-    return finished;
-}
-
-#if B2PT_COOP
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
-                                                        const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
-                                                        unsigned *__restrict__ next, int *__restrict__ hit_prim, float *__restrict__ hit_t,
-                                                        Counters *cnt, double *__restrict__ hit_t64 = nullptr) {
-    const unsigned n = *n_ptr;
-    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
-    unsigned long long refs = 0;
-    TravStats st{0, 0};
-    bool exhausted = false;
-    unsigned idx = 0;
-    Ray r;
-    r.o = r.d = r.inv = mk3(0, 0, 0);
-    Coop C;
-    coop_begin(C);
-    C.has = false;
-    uint2 stk[kStackSize4];
-    Fetch F = fetch_begin(n);
-    for (;;) {
-        if (!exhausted) {
-            // the leaders of idle groups take new rays; the index is handed to the other three lanes
-            unsigned got = fetch_rays(F, !C.has && c == 0u, n, next, lane);
-            got = __shfl_sync(kFull, got, gl);
-            if (!C.has && got != 0xFFFFFFFFu) {
-                idx = got;
-                const float4 o = qo[idx], d = qd[idx];
-                r = make_ray(xyz(o), xyz(d));
-                if (c == 0u) refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
-                    if (c == 0u) {  // rare: the reference's own topology, one lane
-                        Hit h;
-                        binary_walk<COUNT>(S, r, &h, &st);
-                        hit_prim[idx] = h.prim;
-                        hit_t[idx] = (float)h.t;
-                        if (hit_t64) hit_t64[idx] = h.t;
-                    }
-                } else {
-                    coop_begin(C);
-                }
-            }
-            exhausted = F.dry && F.lo >= F.hi;
-        }
-        unsigned act = __ballot_sync(kFull, C.has);
-        if (!act) {
-            if (exhausted) break;
-            continue;
-        }
-        do {
-            if (coop_step<COUNT>(S, r, C, stk, &st) && c == 0u) {
-                hit_prim[idx] = C.h.prim;
-                hit_t[idx] = (float)C.h.t;  // Ray::operator()(double t) converts t to float before use
-                if (hit_t64) hit_t64[idx] = C.h.t;  // the parity entry point wants Intersection::distance itself
-            }
-            act = __ballot_sync(kFull, C.has);
-        } while (act && (exhausted || __popc(act) > 4 * B2PT_COOP_REFILL));
-    }
-    refs = warp_sum(refs);
-    unsigned long long nodes = st.nodes, prims = st.prims;
-    if (COUNT) { nodes = warp_sum(nodes); prims = warp_sum(prims); }
-    if (lane == 0) {
-        if (refs) atomicAdd(&cnt->rays_reference, refs);
-        if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
-    }
-}
-#else
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(SceneView S, const float4 *__restrict__ qo, const float4 *__restrict__ qd,
                                                         const uint32_t *__restrict__ qinfo, const unsigned *__restrict__ n_ptr,
@@ -494,14 +316,14 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
                 float4 o = qo[idx], d = qd[idx];
                 r = make_ray(xyz(o), xyz(d));
                 refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
+                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
                     Hit h;
                     binary_walk<COUNT>(S, r, &h, &st);
                     hit_prim[idx] = h.prim;
                     hit_t[idx] = (float)h.t;
                     if (hit_t64) hit_t64[idx] = h.t;
                 } else {
-                    trav4_begin(T);
+                    trav4_begin(T, r);
                     has = true;
                 }
             }
@@ -530,8 +352,6 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
         if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
     }
 }
-
-#endif
 
 // Geometry of the hit the shading kernels need (Intersection::coords / normal).
 __device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int prim, float tf, f3 *p, f3 *n, uint32_t *mat, uint32_t *kind) {
@@ -700,145 +520,60 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
 }
 
 // ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
-// The visibility decision walked by four lanes per shadow ray, like the extend kernel (coop_step): lane c loads and tests child c
-// of the group's quad; leaf children whose box passed are tested by their lanes at once — in the window search (phase 1) any hit
-// inside the window restarts the group as the occluder search, in the occluder search (phase 2) any hit with t < dist outside
-// the window ends it — which is order-independent, so the decision is the one pt::shadow_step takes.
-#ifndef B2PT_COOP_SHADOW
-#define B2PT_COOP_SHADOW 1
+// B2PT_SHADOW_WIDE 1 (default): the walk over the compressed four-wide quads (pt::shadow4_step); 0: the binary walk over the SAH
+// tree with the reference's box arithmetic (pt::shadow_step), kept for A/B runs.
+#ifndef B2PT_SHADOW_WIDE
+#define B2PT_SHADOW_WIDE 1
 #endif
-#if B2PT_COOP_SHADOW
-struct CoopShadow {
-    float dist, lo, hi;
-    uint32_t quad;
-    int level, sp, phase;
-    bool has;
-};
-__device__ __forceinline__ void coop_shadow_begin(CoopShadow &C, float dist, int phase) {
-    const float m = 4e-3f + 1e-5f * dist;
-    C.dist = dist; C.lo = dist - m; C.hi = dist + m;
-    C.quad = 0; C.level = 0; C.sp = 0; C.phase = phase;
-    C.has = true;
-}
-// Returns 0 while the group keeps walking (or idles), 1 when it has just finished with "visible", 2 with "not visible".
-template <bool COUNT>
-__device__ __forceinline__ int coop_shadow_step(const SceneView &S, const Ray &r, CoopShadow &C, uint32_t *stk, TravStats *st) {
-    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
-    float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
-    if (C.has) {
-        const float4 *p = S.nodes4 + 8 * (size_t)C.quad + 2 * c;
-        lo4 = PT_LDG4(p); hi4 = PT_LDG4(p + 1);
-    }
-    float t = 0.f, x = 0.f;
-    const bool hit = C.has && box_hit2(xyz(lo4), xyz(hi4), r, &t, &x) && !(t > C.hi) && !(C.phase == 1 && x < C.lo);
-    const uint32_t a = f2u(lo4.w);
-    const unsigned meta = __shfl_sync(kFull, f2u(hi4.w), gl) >> 8;
-    const unsigned ghit = (__ballot_sync(kFull, hit) >> gl) & 15u;
-    const bool is_leaf = (meta >> c) & 1u;
-    if (COUNT && C.has) st->nodes += 1;
-    int result = 0;
-    bool restarted = false;
-    if (__any_sync(kFull, (ghit & meta & 15u) != 0u)) {
-        bool inside_hit = false, occluder = false;
-        if (hit && is_leaf) {
-            double tt;
-            if (COUNT) st->prims++;
-            if (prim_hit(S, a, ((meta >> (4 + c)) & 1u) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &tt)) {
-                const bool inside = fabs(tt - (double)C.dist) < (double)kEps;
-                inside_hit = inside;
-                occluder = !inside && tt < (double)C.dist;
-            }
-        }
-        const unsigned g_in = (__ballot_sync(kFull, inside_hit) >> gl) & 15u, g_oc = (__ballot_sync(kFull, occluder) >> gl) & 15u;
-        if (C.has) {
-            if (C.phase == 1) {
-                restarted = g_in != 0u;  // W holds: restart as the occluder search (below; every lane must reach the shuffles)
-            } else if (g_oc) {  // a closer hit outside the window: the closest hit fails the test (Scene.cpp:74-75)
-                C.has = false;
-                result = 2;
-            }
-        }
-    }
-    const bool cand = C.has && !restarted && hit && !is_leaf;
-    const uint32_t key = cand ? ((nonneg_bits(t) & ~3u) | c) : 0xFFFFFFFFu;
-    uint32_t kmin = min(key, __shfl_xor_sync(kFull, key, 1));
-    kmin = min(kmin, __shfl_xor_sync(kFull, kmin, 2));
-    const uint32_t a_next = __shfl_sync(kFull, a, gl + (kmin & 3u));
-    const bool descend = C.has && !restarted && kmin != 0xFFFFFFFFu;
-    if (descend) {
-        if (cand && c != (kmin & 3u)) stk[C.sp++] = a | ((uint32_t)(C.level + 1) << 24);
-        C.quad = a_next;
-        C.level++;
-    }
-    if (restarted) { C.phase = 2; C.sp = 0; C.quad = 0; C.level = 0; }
-    const bool need_pop = C.has && !restarted && !descend;
-    if (__any_sync(kFull, need_pop)) {
-        uint32_t pk = 0, ex = 0;
-        if (need_pop && C.sp > 0) {
-            ex = stk[C.sp - 1];
-            pk = ((ex >> 24) << 2) | (3u - c);
-        }
-        uint32_t pmax = max(pk, __shfl_xor_sync(kFull, pk, 1));
-        pmax = max(pmax, __shfl_xor_sync(kFull, pmax, 2));
-        const unsigned winner = 3u - (pmax & 3u);
-        const uint32_t wx = __shfl_sync(kFull, ex, gl + winner);
-        if (need_pop) {
-            if (pmax == 0u) {  // nothing left: no occluder (phase 2) / no witness (phase 1)
-                C.has = false;
-                result = C.phase == 2 ? 1 : 2;
-            } else {
-                if (c == winner) --C.sp;
-                C.quad = wx & 0xFFFFFFu;
-                C.level = (int)(wx >> 24);
-            }
-        }
-    }
-    return result;
-}
+#if B2PT_SHADOW_WIDE
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(SceneView S, const float4 *__restrict__ sh_o, const float4 *__restrict__ sh_d,
                                                         const unsigned *__restrict__ n_ptr, unsigned *__restrict__ next,
                                                         unsigned char *__restrict__ vis, Counters *cnt) {
     const unsigned n = *n_ptr;
-    const unsigned lane = threadIdx.x & 31u, c = lane & 3u, gl = lane & ~3u;
+    const unsigned lane = threadIdx.x & 31u;
     TravStats st{0, 0};
-    bool exhausted = false;
+    bool has = false, exhausted = false;
     unsigned slot = 0;  // where the decision goes (sh_base[vertex] + sample)
+    float dist = 0.f;
     Ray r;
+    ShadowTrav4 T;
+    uint32_t T_stack[kStackSize4];
+    T.stk = T_stack;
     r.o = r.d = r.inv = mk3(0, 0, 0);
-    CoopShadow C;
-    coop_shadow_begin(C, 0.f, 2);
-    C.has = false;
-    uint32_t stk[kStackSize4];
+    shadow4_begin(T, 0.f, 2);
     Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
-            unsigned got = fetch_rays(F, !C.has && c == 0u, n, next, lane);
-            got = __shfl_sync(kFull, got, gl);
-            if (!C.has && got != 0xFFFFFFFFu) {
+            const unsigned got = fetch_rays(F, !has, n, next, lane);
+            if (!has && got != 0xFFFFFFFFu) {
                 const float4 o = sh_o[got], d = sh_d[got];
                 r = make_ray(xyz(o), xyz(d));
+                dist = o.w;
                 const uint32_t tag = __float_as_uint(d.w);
                 const int phase = (tag & 0x80000000u) ? 1 : 2;
                 slot = tag & 0x7FFFFFFFu;
-                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
-                    if (c == 0u) vis[slot] = binary_visible<COUNT>(S, r, o.w, phase, &st) ? 1 : 0;
+                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
+                    vis[slot] = binary_visible<COUNT>(S, r, dist, phase, &st) ? 1 : 0;
                 } else {
-                    coop_shadow_begin(C, o.w, phase);
+                    shadow4_begin(T, r, dist, phase);
+                    has = true;
                 }
             }
             exhausted = F.dry && F.lo >= F.hi;
         }
-        unsigned act = __ballot_sync(kFull, C.has);
+        unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) {
             if (exhausted) break;
             continue;
         }
         do {
-            const int res = coop_shadow_step<COUNT>(S, r, C, stk, &st);
-            if (res && c == 0u) vis[slot] = res == 1 ? 1 : 0;
-            act = __ballot_sync(kFull, C.has);
-        } while (act && (exhausted || __popc(act) > 4 * B2PT_COOP_REFILL));
+            if (has && !shadow4_step<COUNT>(S, r, dist, T, &st)) {
+                vis[slot] = T.visible ? 1 : 0;
+                has = false;
+            }
+            act = __ballot_sync(0xffffffffu, has);
+        } while (act && (exhausted || __popc(act) > kRefillBelow));
     }
     if (COUNT) {
         unsigned long long nodes = warp_sum((unsigned long long)st.nodes), prims = warp_sum((unsigned long long)st.prims);
@@ -1878,8 +1613,9 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_entries, const float4 *, 19, packed.lt_entries.data(), 16 * packed.lt_entries.size());
     UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
-    UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
-    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.nodes.data(), sizeof(b2pt_node) * packed.quads.nodes.size());
+    UP(leaf, const float4 *, 22, packed.leaf.data(), 16 * packed.leaf.size());
+    if (!packed.quads.q8.empty()) UP(nodes4, const float4 *, 23, packed.quads.q8.data(), 4 * packed.quads.q8.size());
+    v.quad_o_max = packed.quads.o_max;
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;
