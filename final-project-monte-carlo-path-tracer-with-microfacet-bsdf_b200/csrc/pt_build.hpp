@@ -176,93 +176,9 @@ struct SahBuilder {
 struct QuadTree {
     std::vector<b2pt_node> nodes;  // 4 per quad, root = quad 0
     int stack_need = 0;            // entries a depth-first walk can hold at once (<= sum over a path of interior children - 1)
-    int depth = 0;                 // quads on the longest root-to-leaf chain minus one
-    // The form the kernels walk (pt::quad_slabs): 16 words = 64 bytes per quad,
-    //   words 0-2: origin (float3); word 3: biased step exponents ex | ey << 8 | ez << 16 | (leaf mask | sphere mask << 4) << 24
-    //   words 4-7: the four child words (quad index / primitive id)
-    //   words 8-13: lo.x, hi.x, lo.y, hi.y, lo.z, hi.z — one byte per child (child i in byte i): plane = origin + byte * 2^e
-    // EMPTY slots carry lo = 255, hi = 0 on every axis (an inverted box: near > far whatever the ray).
-    std::vector<uint32_t> q8;
-    float o_max = 0.f;             // largest ray-origin component the error budget below covers
+    int depth = 0;                 // quads on the longest root-to-leaf chain minus one (the four-lane walk keeps one stack entry per
+                                   // depth and lane, and carries the depth in six bits of its pop key)
 };
-// Compression of the quads.  Per quad and axis the children's planes are written as origin + byte * s with s = 2^e the smallest
-// power of two that spans the quad in 250 steps, but not below s_min; lo bytes are rounded down and hi bytes up, and then each is
-// moved OUT by one more step, so the stored box exceeds the exact one by between s and 2s on every side.
-//
-// Error budget (u = 2^-24, per plane, A = inv * s exactly): the kernel computes t' = fl(fma(2^23 + byte, A, N)) with
-// N = fl(fma(-2^23, A, B)), B = fl(fma(origin, inv, -fl(o inv))) (far planes: B + EPSILON first).  N is a number of magnitude
-// 2^23 |A| (1 + 1/8 at most, because 2^23 s >= 8 (o_max + p_max) >= 8 |origin - o|), so its rounding costs up to 0.57 |A|; B's
-// two roundings cost u |inv| (|o| + |origin - o|) and the final rounding u |t|.  The reference computes fl(fl(plane - o) inv), off by
-// at most 2u |inv| (|plane| + |o|).  Together: 0.57 |A| + 5u |inv| (o_max + p_max), against a margin of one step |A| = |inv| s.
-// s >= s_min = 2^-19 (o_max + p_max) = 32u (...) leaves 0.43 |A| >= 13u |inv| (o_max + p_max) for the second term, so every near
-// value is <= and every far value >= what the reference computes for any box inside the exact one: the compressed test cannot
-// fail where the reference's test of a contained box passes (max / min and the comparisons are monotone).
-// o_max = 4 x the scene's largest coordinate; rays from further away take the exact binary walk.
-inline bool make_q8(QuadTree &qt) {
-    qt.q8.clear();
-    if (qt.nodes.empty()) return false;
-    double p_max = 1.0;
-    for (const b2pt_node &n : qt.nodes) {
-        if ((n.kind & 0xFFu) == B2PT_NODE_EMPTY) continue;
-        for (int k = 0; k < 3; ++k) {
-            if (!(std::fabs(n.bmin[k]) < INFINITY) || !(std::fabs(n.bmax[k]) < INFINITY)) return false;  // non-finite boxes: exact walks only
-            p_max = std::fmax(p_max, std::fmax(std::fabs((double)n.bmin[k]), std::fabs((double)n.bmax[k])));
-        }
-    }
-    const double o_max = 4.0 * p_max;
-    const int e_min = (int)std::ceil(std::log2(o_max + p_max)) - 19;
-    qt.o_max = (float)o_max;
-    const size_t nq = qt.nodes.size() / 4;
-    qt.q8.assign(nq * 16, 0u);
-    for (size_t q = 0; q < nq; ++q) {
-        uint32_t *w = &qt.q8[q * 16];
-        uint32_t meta = 0, rows[6] = {0, 0, 0, 0, 0, 0}, exps = 0;
-        for (int i = 0; i < 4; ++i) {
-            const b2pt_node &n = qt.nodes[4 * q + i];
-            const uint32_t kind = n.kind & 0xFFu;
-            w[4 + i] = n.a;
-            if (kind == B2PT_NODE_TRIANGLE || kind == B2PT_NODE_SPHERE) meta |= 1u << i;
-            if (kind == B2PT_NODE_SPHERE) meta |= 16u << i;
-        }
-        for (int k = 0; k < 3; ++k) {
-            double lo_min = INFINITY, hi_max = -INFINITY;
-            for (int i = 0; i < 4; ++i) {
-                const b2pt_node &n = qt.nodes[4 * q + i];
-                if ((n.kind & 0xFFu) == B2PT_NODE_EMPTY) continue;
-                lo_min = std::fmin(lo_min, (double)n.bmin[k]); hi_max = std::fmax(hi_max, (double)n.bmax[k]);
-            }
-            if (!(lo_min <= hi_max)) { lo_min = 0.0; hi_max = 0.0; }  // a quad of EMPTY slots only (never visited)
-            int e = e_min;
-            if (hi_max > lo_min) e = std::max(e_min, (int)std::ceil(std::log2((hi_max - lo_min) / 250.0)));
-            for (;; ++e) {
-                if (e + 127 < 1 || e + 127 > 254) return false;
-                const double sd = std::ldexp(1.0, e);
-                float origin = (float)(lo_min - 2.0 * sd);
-                if ((double)origin > lo_min - 2.0 * sd) origin = std::nextafter(origin, -INFINITY);
-                bool ok = true;
-                uint32_t lo_row = 0, hi_row = 0;
-                for (int i = 0; i < 4 && ok; ++i) {
-                    const b2pt_node &n = qt.nodes[4 * q + i];
-                    if ((n.kind & 0xFFu) == B2PT_NODE_EMPTY) { lo_row |= 255u << (8 * i); continue; }
-                    const double ql = std::floor(((double)n.bmin[k] - (double)origin) / sd) - 1.0;
-                    const double qh = std::ceil(((double)n.bmax[k] - (double)origin) / sd) + 1.0;
-                    // the stored planes must lie at least one step outside the exact ones (checked in exact arithmetic)
-                    ok = ql >= 0.0 && qh <= 255.0 && (double)origin + ql * sd <= (double)n.bmin[k] - sd && (double)origin + qh * sd >= (double)n.bmax[k] + sd;
-                    lo_row |= (uint32_t)ql << (8 * i);
-                    hi_row |= (uint32_t)qh << (8 * i);
-                }
-                if (!ok) continue;
-                std::memcpy(&w[k], &origin, 4);
-                exps |= (uint32_t)(e + 127) << (8 * k);
-                rows[2 * k] = lo_row; rows[2 * k + 1] = hi_row;
-                break;
-            }
-        }
-        w[3] = exps | (meta << 24);
-        for (int k = 0; k < 6; ++k) w[8 + k] = rows[k];
-    }
-    return true;
-}
 inline float node_half_area(const b2pt_node &n) {
     float dx = n.bmax[0] - n.bmin[0], dy = n.bmax[1] - n.bmin[1], dz = n.bmax[2] - n.bmin[2];
     if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.f;

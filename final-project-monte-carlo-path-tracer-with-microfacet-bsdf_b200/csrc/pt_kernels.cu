@@ -316,14 +316,14 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
                 float4 o = qo[idx], d = qd[idx];
                 r = make_ray(xyz(o), xyz(d));
                 refs += (unsigned)__popc((qinfo[idx] >> INFO_MASK_SHIFT) & 7u);
-                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
                     Hit h;
                     binary_walk<COUNT>(S, r, &h, &st);
                     hit_prim[idx] = h.prim;
                     hit_t[idx] = (float)h.t;
                     if (hit_t64) hit_t64[idx] = h.t;
                 } else {
-                    trav4_begin(T, r);
+                    trav4_begin(T);
                     has = true;
                 }
             }
@@ -520,10 +520,10 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
 }
 
 // ---- shadow: the visibility decision of Scene.cpp:72-75 (persistent warps, dynamic fetch like extend) -----------------
-// B2PT_SHADOW_WIDE 1 (default): the walk over the compressed four-wide quads (pt::shadow4_step); 0: the binary walk over the SAH
-// tree with the reference's box arithmetic (pt::shadow_step), kept for A/B runs.
+// B2PT_SHADOW_WIDE 0 (default): the binary walk over the SAH tree (pt::shadow_step) — any-hit rays stop early, so a quad step tests
+// 40 % more boxes than the pair steps it replaces and measures 3-6 % slower (r01, r02e); 1: the four-wide walk (pt::shadow4_step).
 #ifndef B2PT_SHADOW_WIDE
-#define B2PT_SHADOW_WIDE 1
+#define B2PT_SHADOW_WIDE 0
 #endif
 #if B2PT_SHADOW_WIDE
 template <bool COUNT>
@@ -553,10 +553,10 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
                 const uint32_t tag = __float_as_uint(d.w);
                 const int phase = (tag & 0x80000000u) ? 1 : 2;
                 slot = tag & 0x7FFFFFFFu;
-                if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) {
+                if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) {
                     vis[slot] = binary_visible<COUNT>(S, r, dist, phase, &st) ? 1 : 0;
                 } else {
-                    shadow4_begin(T, r, dist, phase);
+                    shadow4_begin(T, dist, phase);
                     has = true;
                 }
             }
@@ -1308,6 +1308,9 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     // the device has less to give.
     size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : (S.n_dir <= 8 ? (size_t)48 << 20 : (size_t)12 << 20);
     if (wave > total) wave = (size_t)std::max<unsigned long long>(total, 1);
+    // short jobs: a queue of a sixth of the job (but at least 2 Mi rays) keeps the bounce count low enough and spares the
+    // allocation of tens of gigabytes of wave state for a render that lasts a few milliseconds (profiles/r02g_phases_*)
+    if (p->max_wave_bundles <= 0) wave = std::min<size_t>(wave, (size_t)std::max<unsigned long long>(total / 6, (unsigned long long)2 << 20));
     // Visibility slots are numbered up to 3 * wave * n_dir and share a 32-bit word with the phase flag of the shadow queue
     // (bit 31), and the slot counter itself is 32 bits wide: the queue is kept short enough for both.
     const size_t slot_limit = ((size_t)1 << 31) / (3 * (size_t)S.n_dir) / kBlock * kBlock;
@@ -1613,9 +1616,8 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_entries, const float4 *, 19, packed.lt_entries.data(), 16 * packed.lt_entries.size());
     UP(lt_off, const int *, 20, packed.lt_off.data(), 4 * packed.lt_off.size());
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
-    UP(leaf, const float4 *, 22, packed.leaf.data(), 16 * packed.leaf.size());
-    if (!packed.quads.q8.empty()) UP(nodes4, const float4 *, 23, packed.quads.q8.data(), 4 * packed.quads.q8.size());
-    v.quad_o_max = packed.quads.o_max;
+    UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
+    if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.nodes.data(), sizeof(b2pt_node) * packed.quads.nodes.size());
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;

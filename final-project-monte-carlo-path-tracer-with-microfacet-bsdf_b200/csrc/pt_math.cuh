@@ -209,15 +209,12 @@ struct Material {
 struct SceneView {
     const float4 *nodes;      // traversal tree built by pt_build.hpp (binned SAH over the reference's leaves); 2 float4 per node:
                               // (bmin, a) (bmax, kind); EMPTY nodes carry NaN boxes, which fail the box test by themselves
-    const float4 *nodes4;     // `nodes` collapsed four-wide and compressed (pt_build.hpp: make_q8), 4 float4 = 64 bytes per quad: origin +
-                              // step exponents + masks, four child words, six rows of one byte per child; null when the collapse needs a
-                              // deeper stack than kStackSize4 (then every ray takes the binary walk)
-    const float4 *leaf;       // per primitive, 5 float4: its exact reference leaf box (bmin, bmax) and (v0, e1, e2) — what a leaf child
-                              // that passed the compressed test is tested with, and what every primitive test reads
-    float quad_o_max;         // rays whose origin has a larger component than this (or an inverse direction beyond kInvMax) take the binary walk
+    const float4 *nodes4;     // `nodes` collapsed four-wide (pt_build.hpp): 8 float4 per quad = one 128-byte line per step; null when the
+                              // collapse needs a deeper stack than kStackSize4 (then every ray takes the binary walk)
     const float4 *nodes_ref;  // the reference's own topology (src/BVH.cpp:27-93), same layout: used by rays whose slab
                               // products can be NaN (see ray_needs_reference_tree) and by the parity entry points
     const float4 *v0, *e1, *e2, *nrm;  // per primitive
+    const float4 *tri;                 // per primitive, interleaved (v0, e1, e2): the three loads of a primitive test hit one or two lines
     const float *v1v2, *uv;            // 6 floats per primitive
     const uint32_t *prim_mat, *prim_kind;
     const Material *mats;
@@ -351,7 +348,7 @@ PT_HD float prune_bound(double best) {
 
 // primitive test of a leaf: Triangle::getIntersection or Sphere::getIntersection
 PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
-    const float4 *q = S.leaf + 5 * (size_t)prim + 2;
+    const float4 *q = S.tri + 3 * (size_t)prim;
     float4 a = PT_LDG4(q);
     float4 b = PT_LDG4(q + 1);
     if (kind == NODE_TRIANGLE) {
@@ -445,114 +442,15 @@ PT_HD Hit closest_hit(const SceneView &S, const Ray &r, TravStats *st) {
     return T.h;
 }
 
-// ---- the walk over the compressed four-wide tree ---------------------------------------------------------------------------
-// ncu (profiles/r01q, r02b): the one-lane-per-ray walk is bound by the L1 data pipe — every lane reads its own 128-byte quad with
-// eight 16-byte loads, one L1 wavefront each, at a 79 % hit rate — not by arithmetic (halving the box arithmetic changed nothing,
-// profiles/r02c).  So the quads are made SMALL: 64 bytes = four loads per step (half the wavefronts, half the working set):
-//     word 0-2: origin (float3)        word 3: the three power-of-two step exponents (biased, one byte each) | meta << 24
-//     word 4-7: the four child words (quad index / primitive id)
-//     word 8-13: lo.x, hi.x, lo.y, hi.y, lo.z, hi.z of the four children as one BYTE each: plane = origin + byte * 2^e
-// Interior boxes only steer the walk — a primitive is tested iff ITS OWN leaf box passes the reference's test (pt_build.hpp) — so
-// they may be any boxes that contain the exact ones, tested with any arithmetic that cannot fail where the reference's test of a
-// box inside passes.  The bytes are rounded outwards and then moved out by one more step (pt_build.hpp: make_q8, with the
-// error budget), and a plane costs two instructions: the byte is dropped into the mantissa of 2^23 (PRMT) and
-//     t = fma(2^23 + byte, inv * 2^e, (origin - o) * inv - 2^23 * inv * 2^e)
-// against near / far rows picked by the direction's sign, with EPSILON folded into the far addend:
-//     near = max3(tnx, tny, tnz),  far = min3(tfx, tfy, tfz),  pass <=> near <= far and far >= 0
-// which is Bounds3::IntersectP's  tmin - EPSILON <= tmax && tmax >= -EPSILON  on the wider box.  A leaf child that passes is
-// then tested exactly — the reference's box test on its exact leaf box, then the primitive — so candidates, hits and t are the
-// reference's.  Rays outside the budget's assumptions (|o| > quad_o_max, |1/d| > kInvMax, NaN slab products) take the binary
-// walk with the reference's arithmetic.
-constexpr float kInvMax = 1e18f;
-PT_HD bool ray_needs_exact_walk(const SceneView &S, const Ray &r) {
-    const float s = fmaxf(fmaxf(fabsf(r.inv.x), fabsf(r.inv.y)), fabsf(r.inv.z));
-    const float q = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z));
-    return !(s <= kInvMax) || !(q <= S.quad_o_max) || ray_needs_reference_tree(r);
-}
-// What the padded test needs of a ray: the addends -o * inv and the rows to read (0 / 1: lo / hi is the near plane).
-struct RayQ {
-    f3 nb;           // -o * inv
-    int ix, iy, iz;  // 1 when the direction component is negative: the near plane of that axis is the box's hi plane
-};
-PT_HD RayQ make_rayq(const Ray &r) {
-    RayQ q;
-    q.nb = mk3(-(r.o.x * r.inv.x), -(r.o.y * r.inv.y), -(r.o.z * r.inv.z));
-    q.ix = r.inv.x < 0.f ? 1 : 0; q.iy = r.inv.y < 0.f ? 1 : 0; q.iz = r.inv.z < 0.f ? 1 : 0;
-    return q;
-}
-PT_HD float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-PT_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
-// byte c of `word` in the low mantissa bits of 2^23: the float 2^23 + byte
-PT_HD float q8_float(uint32_t word, int c) {
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)c));
-#else
-    return u2f(0x4B000000u | ((word >> (8 * c)) & 0xFFu));
-#endif
-}
-// Entry distances (lower bounds) and exit distances (upper bounds, EPSILON included) of the four children of a quad, its child
-// words and its leaf / sphere masks.
-struct QuadT {
-    float n0, n1, n2, n3, f0, f1, f2, f3;
-    uint32_t a0, a1, a2, a3;
-    unsigned meta;
-};
-PT_HD QuadT quad_slabs(const float4 *p, const Ray &r, const RayQ &q) {
-    const float4 h = PT_LDG4(p), cw = PT_LDG4(p + 1), r2 = PT_LDG4(p + 2), r3 = PT_LDG4(p + 3);
-    const uint32_t bits = f2u(h.w);
-    // per axis: A = inv * 2^e (exact), near addend (origin - o) * inv - 2^23 A, far addend the same with EPSILON added first
-    const float ax = r.inv.x * u2f((bits & 0xFFu) << 23), ay = r.inv.y * u2f(((bits >> 8) & 0xFFu) << 23), az = r.inv.z * u2f(((bits >> 16) & 0xFFu) << 23);
-    const float bx = PT_FMA(h.x, r.inv.x, q.nb.x), by = PT_FMA(h.y, r.inv.y, q.nb.y), bz = PT_FMA(h.z, r.inv.z, q.nb.z);
-    const float nx = PT_FMA(-8388608.f, ax, bx), ny = PT_FMA(-8388608.f, ay, by), nz = PT_FMA(-8388608.f, az, bz);
-    const float fx = PT_FMA(-8388608.f, ax, bx + kEps), fy = PT_FMA(-8388608.f, ay, by + kEps), fz = PT_FMA(-8388608.f, az, bz + kEps);
-    // rows: r2 = (lo.x, hi.x, lo.y, hi.y), r3 = (lo.z, hi.z, -, -); a negative direction component enters through the hi plane
-    const uint32_t wnx = f2u(q.ix ? r2.y : r2.x), wfx = f2u(q.ix ? r2.x : r2.y);
-    const uint32_t wny = f2u(q.iy ? r2.w : r2.z), wfy = f2u(q.iy ? r2.z : r2.w);
-    const uint32_t wnz = f2u(q.iz ? r3.y : r3.x), wfz = f2u(q.iz ? r3.x : r3.y);
-    QuadT t;
-    t.n0 = max3f(PT_FMA(q8_float(wnx, 0), ax, nx), PT_FMA(q8_float(wny, 0), ay, ny), PT_FMA(q8_float(wnz, 0), az, nz));
-    t.n1 = max3f(PT_FMA(q8_float(wnx, 1), ax, nx), PT_FMA(q8_float(wny, 1), ay, ny), PT_FMA(q8_float(wnz, 1), az, nz));
-    t.n2 = max3f(PT_FMA(q8_float(wnx, 2), ax, nx), PT_FMA(q8_float(wny, 2), ay, ny), PT_FMA(q8_float(wnz, 2), az, nz));
-    t.n3 = max3f(PT_FMA(q8_float(wnx, 3), ax, nx), PT_FMA(q8_float(wny, 3), ay, ny), PT_FMA(q8_float(wnz, 3), az, nz));
-    t.f0 = min3f(PT_FMA(q8_float(wfx, 0), ax, fx), PT_FMA(q8_float(wfy, 0), ay, fy), PT_FMA(q8_float(wfz, 0), az, fz));
-    t.f1 = min3f(PT_FMA(q8_float(wfx, 1), ax, fx), PT_FMA(q8_float(wfy, 1), ay, fy), PT_FMA(q8_float(wfz, 1), az, fz));
-    t.f2 = min3f(PT_FMA(q8_float(wfx, 2), ax, fx), PT_FMA(q8_float(wfy, 2), ay, fy), PT_FMA(q8_float(wfz, 2), az, fz));
-    t.f3 = min3f(PT_FMA(q8_float(wfx, 3), ax, fx), PT_FMA(q8_float(wfy, 3), ay, fy), PT_FMA(q8_float(wfz, 3), az, fz));
-    t.a0 = f2u(cw.x); t.a1 = f2u(cw.y); t.a2 = f2u(cw.z); t.a3 = f2u(cw.w);
-    t.meta = bits >> 24;  // leaf mask (bits 0-3), sphere mask (bits 4-7)
-    return t;
-}
-// the exact leaf test of primitive `prim`: the reference's box test on its own leaf box, entry distance in *tl
-PT_HD bool leaf_box_hit(const SceneView &S, uint32_t prim, const Ray &r, float *tl) {
-    const float4 *q = S.leaf + 5 * (size_t)prim;
-    const float4 a = PT_LDG4(q), b = PT_LDG4(q + 1);
-    return box_hit(xyz(a), xyz(b), r, tl);
-}
-PT_HD bool leaf_box_hit2(const SceneView &S, uint32_t prim, const Ray &r, float *tl, float *xl) {
-    const float4 *q = S.leaf + 5 * (size_t)prim;
-    const float4 a = PT_LDG4(q), b = PT_LDG4(q + 1);
-    return box_hit2(xyz(a), xyz(b), r, tl, xl);
-}
-PT_HD bool leaf_prim_hit(const SceneView &S, uint32_t prim, bool sphere, const Ray &r, double *t) {
-    const float4 *q = S.leaf + 5 * (size_t)prim + 2;
-    const float4 a = PT_LDG4(q), b = PT_LDG4(q + 1);
-    if (!sphere) {
-        const float4 c = PT_LDG4(q + 2);
-        double u, v;
-        return tri_hit(xyz(a), xyz(b), xyz(c), r, t, &u, &v);
-    }
-    float tf;
-    const bool ok = sphere_hit(xyz(a), b.x, r, &tf);
-    *t = (double)tf;
-    return ok;
-}
-
+// ---- the same walk over the four-wide tree ------------------------------------------------------------------------------
+// One step = one quad = one 128-byte line: four box tests, the primitive tests of the leaf children that passed (one
+// loop, so lanes with leaves in different slots test together), then the nearest interior child; the others go on the
+// stack with their entry distances.  Same box test, same primitive tests, same pruning margin and tie rule as above.
 struct Trav4 {
     Hit h;
     float bound;
     uint32_t quad;
     int sp;
-    RayQ q;
     uint2 *stk;  // kStackSize4 entries owned by the caller
 };
 PT_HD void trav4_begin(Trav4 &T) {
@@ -562,55 +460,58 @@ PT_HD void trav4_begin(Trav4 &T) {
     T.sp = 0;
     T.quad = 0;
 }
-PT_HD void trav4_begin(Trav4 &T, const Ray &r) {
-    trav4_begin(T);
-    T.q = make_rayq(r);
-}
 // first set bit of a 4-bit mask selects among four registers: predicated selects, no indexing (indexing would put the
 // values in local memory)
 PT_HD float pick4(unsigned m, float a, float b, float c, float d) { return (m & 1u) ? a : ((m & 2u) ? b : ((m & 4u) ? c : d)); }
 PT_HD uint32_t pick4u(unsigned m, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return (m & 1u) ? a : ((m & 2u) ? b : ((m & 4u) ? c : d)); }
 template <bool COUNT>
 PT_HD bool trav4_step(const SceneView &S, const Ray &r, Trav4 &T, TravStats *st) {
-    const QuadT t = quad_slabs(S.nodes4 + 4 * (size_t)T.quad, r, T.q);
+    const float4 *p = S.nodes4 + 8 * (size_t)T.quad;
+    const float4 l0 = PT_LDG4(p), h0 = PT_LDG4(p + 1), l1 = PT_LDG4(p + 2), h1 = PT_LDG4(p + 3);
+    const float4 l2 = PT_LDG4(p + 4), h2 = PT_LDG4(p + 5), l3 = PT_LDG4(p + 6), h3 = PT_LDG4(p + 7);
     if (COUNT) st->nodes += 4;
-    const uint32_t a0 = t.a0, a1 = t.a1, a2 = t.a2, a3 = t.a3;
-    const unsigned meta = t.meta;
-    unsigned hit = ((t.n0 <= fminf(t.f0, T.bound) && t.f0 >= 0.f) ? 1u : 0u) | ((t.n1 <= fminf(t.f1, T.bound) && t.f1 >= 0.f) ? 2u : 0u) |
-                   ((t.n2 <= fminf(t.f2, T.bound) && t.f2 >= 0.f) ? 4u : 0u) | ((t.n3 <= fminf(t.f3, T.bound) && t.f3 >= 0.f) ? 8u : 0u);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    const bool b0 = box_hit(xyz(l0), xyz(h0), r, &t0) && !(t0 > T.bound);
+    const bool b1 = box_hit(xyz(l1), xyz(h1), r, &t1) && !(t1 > T.bound);
+    const bool b2 = box_hit(xyz(l2), xyz(h2), r, &t2) && !(t2 > T.bound);
+    const bool b3 = box_hit(xyz(l3), xyz(h3), r, &t3) && !(t3 > T.bound);
+    const uint32_t a0 = f2u(l0.w), a1 = f2u(l1.w), a2 = f2u(l2.w), a3 = f2u(l3.w);
+    const unsigned meta = f2u(h0.w) >> 8;  // leaf mask (bits 0-3), sphere mask (bits 4-7)
+    unsigned hit = (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u);
     unsigned lm = hit & meta & 15u;
     if (lm) {
         hit ^= lm;
 #pragma unroll 1
         do {
+            const float tl = pick4(lm, t0, t1, t2, t3);
             const uint32_t prim = pick4u(lm, a0, a1, a2, a3);
             const unsigned low = lm & (0u - lm);
             lm ^= low;
-            float tl;
-            if (!leaf_box_hit(S, prim, r, &tl) || tl > T.bound) continue;  // the reference's own test of the leaf box decides
-            double tt;
+            if (tl > T.bound) continue;
+            double t;
             if (COUNT) st->prims++;
-            if (leaf_prim_hit(S, prim, ((meta >> 4) & low) != 0, r, &tt) && (tt < T.h.t || (tt == T.h.t && (int)prim > T.h.prim))) {
-                T.h.t = tt; T.h.prim = (int)prim; T.bound = prune_bound(tt);
+            if (prim_hit(S, prim, ((meta >> 4) & low) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t) &&
+                (t < T.h.t || (t == T.h.t && (int)prim > T.h.prim))) {
+                T.h.t = t; T.h.prim = (int)prim; T.bound = prune_bound(t);
             }
         } while (lm);
         // the bound may have tightened
-        hit &= (t.n0 > T.bound ? 0u : 1u) | (t.n1 > T.bound ? 0u : 2u) | (t.n2 > T.bound ? 0u : 4u) | (t.n3 > T.bound ? 0u : 8u);
+        hit &= (t0 > T.bound ? 0u : 1u) | (t1 > T.bound ? 0u : 2u) | (t2 > T.bound ? 0u : 4u) | (t3 > T.bound ? 0u : 8u);
     }
     if (hit) {
         // nearest interior child next, the others on the stack
         unsigned bm = hit & (0u - hit);
-        float tb = pick4(hit, t.n0, t.n1, t.n2, t.n3);
-        if ((hit & 2u) && t.n1 < tb) { bm = 2u; tb = t.n1; }
-        if ((hit & 4u) && t.n2 < tb) { bm = 4u; tb = t.n2; }
-        if ((hit & 8u) && t.n3 < tb) { bm = 8u; tb = t.n3; }
+        float tb = pick4(hit, t0, t1, t2, t3);
+        if ((hit & 2u) && t1 < tb) { bm = 2u; tb = t1; }
+        if ((hit & 4u) && t2 < tb) { bm = 4u; tb = t2; }
+        if ((hit & 8u) && t3 < tb) { bm = 8u; tb = t3; }
         T.quad = pick4u(bm, a0, a1, a2, a3);
         hit ^= bm;
         if (hit) {
-            if (hit & 1u) T.stk[T.sp++] = make_uint2(a0, f2u(t.n0));
-            if (hit & 2u) T.stk[T.sp++] = make_uint2(a1, f2u(t.n1));
-            if (hit & 4u) T.stk[T.sp++] = make_uint2(a2, f2u(t.n2));
-            if (hit & 8u) T.stk[T.sp++] = make_uint2(a3, f2u(t.n3));
+            if (hit & 1u) T.stk[T.sp++] = make_uint2(a0, f2u(t0));
+            if (hit & 2u) T.stk[T.sp++] = make_uint2(a1, f2u(t1));
+            if (hit & 4u) T.stk[T.sp++] = make_uint2(a2, f2u(t2));
+            if (hit & 8u) T.stk[T.sp++] = make_uint2(a3, f2u(t3));
         }
         return true;
     }
@@ -621,14 +522,14 @@ PT_HD bool trav4_step(const SceneView &S, const Ray &r, Trav4 &T, TravStats *st)
     }
     return false;
 }
-// Scene::intersect: the four-wide walk, or the binary walk with the reference's arithmetic for the rays that need it
+// Scene::intersect: the four-wide walk, or the reference's own topology for the rays that need it
 template <bool COUNT>
 PT_HD Hit closest_hit4(const SceneView &S, const Ray &r, TravStats *st) {
-    if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) return closest_hit<COUNT>(S, r, st);
+    if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) return closest_hit<COUNT>(S, r, st);
     Trav4 T;
     uint2 T_stack[kStackSize4];
     T.stk = T_stack;
-    trav4_begin(T, r);
+    trav4_begin(T);
     while (trav4_step<COUNT>(S, r, T, st)) {}
     return T.h;
 }
@@ -746,7 +647,6 @@ struct ShadowTrav4 {
     float lo, hi;
     uint32_t quad;
     int sp;
-    RayQ q;
     uint32_t *stk;  // kStackSize4 entries owned by the caller
 };
 PT_HD void shadow4_begin(ShadowTrav4 &T, float dist, int phase) {
@@ -757,21 +657,23 @@ PT_HD void shadow4_begin(ShadowTrav4 &T, float dist, int phase) {
     T.quad = 0;
     T.phase = phase;
 }
-PT_HD void shadow4_begin(ShadowTrav4 &T, const Ray &r, float dist, int phase) {
-    shadow4_begin(T, dist, phase);
-    T.q = make_rayq(r);
-}
 // Returns false when the decision is known (T.visible).
 template <bool COUNT>
 PT_HD bool shadow4_step(const SceneView &S, const Ray &r, float dist, ShadowTrav4 &T, TravStats *st) {
     const double eps = (double)kEps, dd = (double)dist;
-    const QuadT t = quad_slabs(S.nodes4 + 4 * (size_t)T.quad, r, T.q);
+    const float4 *p = S.nodes4 + 8 * (size_t)T.quad;
+    const float4 l0 = PT_LDG4(p), h0 = PT_LDG4(p + 1), l1 = PT_LDG4(p + 2), h1 = PT_LDG4(p + 3);
+    const float4 l2 = PT_LDG4(p + 4), h2 = PT_LDG4(p + 5), l3 = PT_LDG4(p + 6), h3 = PT_LDG4(p + 7);
     if (COUNT) st->nodes += 4;
-    const uint32_t a0 = t.a0, a1 = t.a1, a2 = t.a2, a3 = t.a3;
-    const unsigned meta = t.meta;
-    const float lo = T.phase == 1 ? T.lo : 0.f;  // phase 1: only boxes that overlap the window in t can hold a witness (exit >= lo; >= 0 anyway)
-    unsigned hit = ((t.n0 <= fminf(t.f0, T.hi) && t.f0 >= lo) ? 1u : 0u) | ((t.n1 <= fminf(t.f1, T.hi) && t.f1 >= lo) ? 2u : 0u) |
-                   ((t.n2 <= fminf(t.f2, T.hi) && t.f2 >= lo) ? 4u : 0u) | ((t.n3 <= fminf(t.f3, T.hi) && t.f3 >= lo) ? 8u : 0u);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    const float lo = T.phase == 1 ? T.lo : -INFINITY;  // phase 1: only boxes that overlap the window in t can hold a witness
+    const bool b0 = box_hit2(xyz(l0), xyz(h0), r, &t0, &x0) && !(t0 > T.hi) && !(x0 < lo);
+    const bool b1 = box_hit2(xyz(l1), xyz(h1), r, &t1, &x1) && !(t1 > T.hi) && !(x1 < lo);
+    const bool b2 = box_hit2(xyz(l2), xyz(h2), r, &t2, &x2) && !(t2 > T.hi) && !(x2 < lo);
+    const bool b3 = box_hit2(xyz(l3), xyz(h3), r, &t3, &x3) && !(t3 > T.hi) && !(x3 < lo);
+    const uint32_t a0 = f2u(l0.w), a1 = f2u(l1.w), a2 = f2u(l2.w), a3 = f2u(l3.w);
+    const unsigned meta = f2u(h0.w) >> 8;
+    unsigned hit = (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u);
     unsigned lm = hit & meta & 15u;
     hit ^= lm;
 #pragma unroll 1
@@ -779,18 +681,16 @@ PT_HD bool shadow4_step(const SceneView &S, const Ray &r, float dist, ShadowTrav
         const uint32_t prim = pick4u(lm, a0, a1, a2, a3);
         const unsigned low = lm & (0u - lm);
         lm ^= low;
-        float tl, xl;
-        if (!leaf_box_hit2(S, prim, r, &tl, &xl) || tl > T.hi || (T.phase == 1 && xl < T.lo)) continue;
-        double tt;
+        double t;
         if (COUNT) st->prims++;
-        if (leaf_prim_hit(S, prim, ((meta >> 4) & low) != 0, r, &tt)) {
-            const bool inside = fabs(tt - dd) < eps;
+        if (prim_hit(S, prim, ((meta >> 4) & low) ? (uint32_t)NODE_SPHERE : (uint32_t)NODE_TRIANGLE, r, &t)) {
+            const bool inside = fabs(t - dd) < eps;
             if (T.phase == 1) {
                 if (inside) {  // W holds: restart as the occluder search
                     T.phase = 2; T.sp = 0; T.quad = 0;
                     return true;
                 }
-            } else if (!inside && tt < dd) {  // a closer hit outside the window: the closest hit fails the test
+            } else if (!inside && t < dd) {  // a closer hit outside the window: the closest hit fails the test
                 T.visible = false;
                 return false;
             }
@@ -798,10 +698,10 @@ PT_HD bool shadow4_step(const SceneView &S, const Ray &r, float dist, ShadowTrav
     }
     if (hit) {
         unsigned bm = hit & (0u - hit);
-        float tb = pick4(hit, t.n0, t.n1, t.n2, t.n3);
-        if ((hit & 2u) && t.n1 < tb) { bm = 2u; tb = t.n1; }
-        if ((hit & 4u) && t.n2 < tb) { bm = 4u; tb = t.n2; }
-        if ((hit & 8u) && t.n3 < tb) { bm = 8u; tb = t.n3; }
+        float tb = pick4(hit, t0, t1, t2, t3);
+        if ((hit & 2u) && t1 < tb) { bm = 2u; tb = t1; }
+        if ((hit & 4u) && t2 < tb) { bm = 4u; tb = t2; }
+        if ((hit & 8u) && t3 < tb) { bm = 8u; tb = t3; }
         T.quad = pick4u(bm, a0, a1, a2, a3);
         hit ^= bm;
         if (hit) {
@@ -818,13 +718,13 @@ PT_HD bool shadow4_step(const SceneView &S, const Ray &r, float dist, ShadowTrav
 }
 template <bool COUNT>
 PT_HD bool light_visible4(const SceneView &S, const Ray &r, float dist, TravStats *st, int lnode = -1) {
-    if (S.nodes4 == nullptr || ray_needs_exact_walk(S, r)) return light_visible<COUNT>(S, r, dist, st, lnode);
+    if (S.nodes4 == nullptr || ray_needs_reference_tree(r)) return light_visible<COUNT>(S, r, dist, st, lnode);
     int w = window_witness(S, r, dist, lnode);
     if (w == 0) return false;
     ShadowTrav4 T;
     uint32_t T_stack[kStackSize4];
     T.stk = T_stack;
-    shadow4_begin(T, r, dist, w == 1 ? 2 : 1);
+    shadow4_begin(T, dist, w == 1 ? 2 : 1);
     while (shadow4_step<COUNT>(S, r, dist, T, st)) {}
     return T.visible;
 }

@@ -27,7 +27,7 @@ struct PackedScene {
     // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
     // Entry = (bmin, prim id) (bmax, kind): the primitive's own reference leaf box, tested before the primitive.
-    std::vector<float4> leaf;  // per primitive: exact leaf box (bmin, bmax), then (v0, e1, e2) — 5 float4
+    std::vector<float4> tri;  // (v0, e1, e2) per primitive, interleaved
     std::vector<float4> lt_entries;
     std::vector<int> lt_off, lt_cnt;  // cnt < 0: too many neighbours, the window is searched by traversal instead
 };
@@ -100,17 +100,11 @@ inline bool validate_scene(const b2pt_scene_desc *d, std::string &err) {
 }
 
 inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fast_tree = true, const BuildOptions *opt = nullptr) {
-    out.leaf.assign(5 * (size_t)d->n_prims, make_float4(NAN, NAN, NAN, 0.f));  // a primitive without a leaf keeps a NaN box: never tested
+    out.tri.resize(3 * (size_t)d->n_prims);
     for (size_t i = 0; i < d->n_prims; ++i) {
-        std::memcpy(&out.leaf[5 * i + 2], d->prim_v0 + 4 * i, 16);
-        std::memcpy(&out.leaf[5 * i + 3], d->prim_e1 + 4 * i, 16);
-        std::memcpy(&out.leaf[5 * i + 4], d->prim_e2 + 4 * i, 16);
-    }
-    for (uint32_t i = 0; i < d->n_nodes; ++i) {
-        const b2pt_node &n = d->nodes[i];
-        if (n.kind != B2PT_NODE_TRIANGLE && n.kind != B2PT_NODE_SPHERE) continue;
-        out.leaf[5 * (size_t)n.a] = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], 0.f);
-        out.leaf[5 * (size_t)n.a + 1] = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], 0.f);
+        std::memcpy(&out.tri[3 * i], d->prim_v0 + 4 * i, 16);
+        std::memcpy(&out.tri[3 * i + 1], d->prim_e1 + 4 * i, 16);
+        std::memcpy(&out.tri[3 * i + 2], d->prim_e2 + 4 * i, 16);
     }
     out.nodes_ref.assign(d->nodes, d->nodes + d->n_nodes);
     for (auto &n : out.nodes_ref)
@@ -126,11 +120,11 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
     }
     if (out.nodes_fast.empty()) { out.nodes_fast = out.nodes_ref; out.fast_depth = (int)d->max_depth; }
     QuadCollapser(out.nodes_fast, out.quads).run();
-    // the walk needs its stack bound, quad indices that fit a child word, and a compression that succeeded
-    if (out.quads.stack_need + 2 >= kStackSize4 || out.quads.nodes.size() / 4 >= ((size_t)1 << 30) || !make_q8(out.quads)) {
+    // the walks need: the one-lane stack bound, a depth that fits the four-lane walk's per-lane stacks and six-bit depth key, and
+    // quad indices below 2^24 (the stack entries carry the depth in the top byte)
+    if (out.quads.stack_need + 2 >= kStackSize4 || out.quads.depth + 2 >= kStackSize4 || out.quads.depth >= 60 ||
+        out.quads.nodes.size() / 4 >= ((size_t)1 << 24))
         out.quads.nodes.clear();
-        out.quads.q8.clear();
-    }
     {
         // leaf boxes by primitive id
         std::vector<BuildBox> pb(d->n_prims, box_empty_b());

@@ -33,10 +33,8 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     pack_scene(d, h->packed, fast, opt);
     h->nodes.resize(2 * h->packed.nodes_fast.size());
     std::memcpy(h->nodes.data(), h->packed.nodes_fast.data(), sizeof(b2pt_node) * h->packed.nodes_fast.size());
-    if (!h->packed.quads.q8.empty()) {
-        h->nodes4.resize(h->packed.quads.q8.size() / 4);
-        std::memcpy(h->nodes4.data(), h->packed.quads.q8.data(), 4 * h->packed.quads.q8.size());
-    }
+    h->nodes4.resize(2 * h->packed.quads.nodes.size());
+    if (!h->nodes4.empty()) std::memcpy(h->nodes4.data(), h->packed.quads.nodes.data(), sizeof(b2pt_node) * h->packed.quads.nodes.size());
     h->nodes_ref.resize(2 * h->packed.nodes_ref.size());
     std::memcpy(h->nodes_ref.data(), h->packed.nodes_ref.data(), sizeof(b2pt_node) * h->packed.nodes_ref.size());
     auto cp4 = [&](std::vector<float4> &dst, const float *src) { dst.resize(d->n_prims); std::memcpy(dst.data(), src, 16 * (size_t)d->n_prims); };
@@ -58,8 +56,7 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     v.mats = h->packed.mats.data();
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
     v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
-    v.leaf = h->packed.leaf.data();
-    v.quad_o_max = h->packed.quads.o_max;
+    v.tri = h->packed.tri.data();
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     for (int k = 0; k < 3; ++k) v.light_c[k] = h->packed.light_sphere[k];
     v.light_r = h->packed.light_sphere[3];
