@@ -32,6 +32,7 @@ SMOOTH_CONDUCTOR, ROUGH_CONDUCTOR, SMOOTH_DIELECTRIC, ROUGH_DIELECTRIC = 0, 1, 2
 FLAG_COUNT_TRAVERSAL = 1
 FLAG_SPLIT_WAVELENGTHS = 2
 FLAG_FRESH_FRAME = 4
+FLAG_INDEPENDENT_WAVELENGTHS = 8
 FIX_DIRECT_LIGHT_SAMPLE, FIX_MODEL_QUALITY, FIX_ADD_DIAMOND, FIX_OUTPUT_PATH = 1, 2, 4, 8
 NAMED_MATERIALS = ["rough_red_conductor", "rough_white_conductor", "green_mirror", "gold_conductor", "silver_mirror",
                    "smooth_glass", "smooth_glass_gem", "clear_rough_plastic", "rough_plastic"]

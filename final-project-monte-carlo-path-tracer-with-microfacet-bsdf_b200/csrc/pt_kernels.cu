@@ -60,7 +60,16 @@ constexpr int CLASS_TERMINAL = 0;
 constexpr uint32_t INFO_DIM_MASK = 0xFFFFFu;  // bits 0-19: next draw of the path stream
 constexpr int INFO_MASK_SHIFT = 20;            // bits 20-22: wavelength paths on this ray
 constexpr uint32_t INFO_PRIMARY = 1u << 23;    // depth == 0
-constexpr int INFO_DEPTH_SHIFT = 24;           // bits 24-31: depth (saturating, statistics only)
+constexpr int INFO_DEPTH_SHIFT = 24;           // bits 24-30: depth (saturating at 127, statistics only)
+constexpr uint32_t INFO_INDEP = 1u << 31;      // B2PT_FLAG_INDEPENDENT_WAVELENGTHS: the ray's single wavelength path reads its OWN stream
+// Stream tag of the path draws of a ray: the shared stream, or — independent-wavelength mode, where every ray carries one path —
+// a stream of its own per wavelength (tags 0, 2, 3; tag 1 is the camera stream), which gives R, G and B the independent draws the
+// reference's three castRay calls consume (src/Renderer.cpp:77-79).
+__device__ __forceinline__ uint32_t path_tag(uint32_t info) {
+    if (!(info & INFO_INDEP)) return STREAM_PATH;
+    const uint32_t mask = (info >> INFO_MASK_SHIFT) & 7u;
+    return mask == 1u ? 0u : (mask == 2u ? 2u : 3u);
+}
 
 thread_local std::string g_create_error;
 
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
                 q.o[p + k] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
                 q.d[p + k] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample));
                 q.slot[p + k] = slot;
-                q.info[p + k] = INFO_PRIMARY | (mask << INFO_MASK_SHIFT);
+                q.info[p + k] = INFO_PRIMARY | (mask << INFO_MASK_SHIFT) | (gp.split > 1 ? INFO_INDEP : 0u);
             }
         }
     }
@@ -396,7 +405,7 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
                     // microfacet-normal and light-sample draws, Scene.cpp:121): vertices that end here and vertices that
                     // continue are shaded by different kernels, so neither runs half-empty warps.
                     const uint32_t dim_rr = (info & INFO_DIM_MASK) + (mat_is_rough(m) ? 2u : 0u) + 4u * ndir;
-                    Stream rr_s = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), STREAM_PATH, dim_rr);
+                    Stream rr_s = stream_open(k0, k1, __float_as_uint(o4.w), __float_as_uint(d4.w), path_tag(info), dim_rr);
                     const bool survives = stream_next(rr_s) < S.rr_rate;
                     cls = 1 + 2 * m.type + (survives ? 1 : 0);
                     shaded = true;
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
             f3 pn = p + nn * kEps;  // inter.coords += n * EPSILON, Scene.cpp:114
             uint32_t dim = (info & INFO_DIM_MASK) + (mat_is_rough(S.mats[mat]) ? 2u : 0u);
             const unsigned v = vb / ndir;
-            vtx_pn[v] = make_float4(pn.x, pn.y, pn.z, __uint_as_float(dim));
+            vtx_pn[v] = make_float4(pn.x, pn.y, pn.z, __uint_as_float((dim & INFO_DIM_MASK) | (path_tag(info) << 20)));  // stream position | stream tag
             vtx_ps[v] = make_uint2(__float_as_uint(o4.w), __float_as_uint(d4.w));
             vtx_ray[v] = i;
         }
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
             const float4 a = vtx_pn[v];
             const uint2 ps = vtx_ps[v];
             pn = xyz(a);
-            Stream rs = stream_open(k0, k1, ps.x, ps.y, STREAM_PATH, __float_as_uint(a.w) + 4u * k);
+            Stream rs = stream_open(k0, k1, ps.x, ps.y, __float_as_uint(a.w) >> 20, (__float_as_uint(a.w) & INFO_DIM_MASK) + 4u * k);
             float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
             g = nee_geometry(S, pn, u0, u1, u2, u3);
             // A sample whose summand Le * f * cos * cos' / d^2 / pdf / N is zero whatever its visibility (Material::eval returns
@@ -680,7 +689,7 @@ __global__ void __launch_bounds__(kBlock) nee_eval_kernel(SceneView S, Queue q, 
         const Material &m = S.mats[sf.mat];
         const f3 wo = -r.d;
         const bool inner = dot(wo, sf.n) < 0;
-        Stream rs = stream_open(k0, k1, ps.x, ps.y, STREAM_PATH, __float_as_uint(a.w) + 4u * k);
+        Stream rs = stream_open(k0, k1, ps.x, ps.y, __float_as_uint(a.w) >> 20, (__float_as_uint(a.w) & INFO_DIM_MASK) + 4u * k);
         float u0 = stream_next(rs), u1 = stream_next(rs), u2 = stream_next(rs), u3 = stream_next(rs);
         const NeeGeom g = nee_geometry(S, xyz(a), u0, u1, u2, u3);
         const f3 term = nee_term3(m, g, wo, sf.n, sf.u, sf.v, !inner, (int)ndir, mask);  // Material::eval shared by the wavelengths
@@ -784,7 +793,7 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
         if (li < n) {
             const unsigned i = list[li];
             load_ray_state(qi, i, rs);
-            const uint32_t depth = rs.info >> INFO_DEPTH_SHIFT;
+            const uint32_t depth = (rs.info >> INFO_DEPTH_SHIFT) & 127u;
             float *acc = sp.acc + 3 * (size_t)rs.slot;
             Hit h;
             h.prim = hit_prim[i]; h.t = (double)hit_t[i];
@@ -799,7 +808,7 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
                     if (j < rs.nch) rs.phi[j] = phi_compose(rs.phi[j], rs.pend_A[j], rs.pend_f[j]);
             }
             const f3 nrm = s.n;
-            Stream st = stream_open(sp.k0, sp.k1, rs.pixel, rs.sample, STREAM_PATH, rs.info & INFO_DIM_MASK);
+            Stream st = stream_open(sp.k0, sp.k1, rs.pixel, rs.sample, path_tag(rs.info), rs.info & INFO_DIM_MASK);
             f3 mfn = nrm;  // Material::sample, Material.hpp:268-281
             if (ROUGH) {
                 float a = stream_next(st), b = stream_next(st);
@@ -892,8 +901,8 @@ __global__ void __launch_bounds__(kBlock, B2PT_SHADE_MIN_BLOCKS) shade_kernel(Sc
                     lvl_e[j] = ev;
                     lvl_f[j] = f;
                 }
-                uint32_t nd = depth < 255u ? depth + 1u : 255u;
-                new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT);
+                uint32_t nd = depth < 127u ? depth + 1u : 127u;
+                new_info = (new_dim & INFO_DIM_MASK) | (nd << INFO_DEPTH_SHIFT) | (rs.info & INFO_INDEP);
                 // Whatever the rest of the path returns, this level returns A + clamp(0, 5, .) in [A, A + 5] (Scene.cpp:147,174,
                 // 180-183; NaN -> 5).  The map from this level's value to the pixel is monotone (affine, then clamped), so when
                 // it takes the same value at both ends of that interval — an outer clamp is saturated, typically by a brightly
@@ -1287,7 +1296,9 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     const SceneView &S = ctx->view;
     const Camera dcam = make_camera(cam);
     const bool count = (p->flags & B2PT_FLAG_COUNT_TRAVERSAL) != 0;
-    const int split = (p->flags & B2PT_FLAG_SPLIT_WAVELENGTHS) ? 1 : 0;
+    // 0: the three wavelength paths of a sample share rays while their geometry coincides; 1: three rays from the camera on, same
+    // stream (a self-check); 2: three rays AND three streams (the reference's independent draws per castRay call)
+    const int split = (p->flags & B2PT_FLAG_INDEPENDENT_WAVELENGTHS) ? 2 : ((p->flags & B2PT_FLAG_SPLIT_WAVELENGTHS) ? 1 : 0);
 
     GenParams gp{};
     gp.mode = job.mode;

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b2pt.h"
@@ -87,6 +88,19 @@ int main(int argc, char **argv) {
     }
     if (const char *ad = std::getenv("B2PT_ASSET_DIR")) b2pt_host_set_asset_dir(ad);
 
+    // Creating the CUDA contexts takes 1-2 s (driver initialisation + context: profiles/r02g_ctx_time.txt), more than everything the
+    // host does before it needs them (scene assembly 0.1-0.4 s, trees 0.2 s): it runs on its own thread meanwhile.
+    std::vector<b2pt_ctx *> ctxs(gpus, nullptr);
+    std::vector<int> create_rc(gpus, B2PT_OK);
+    std::string create_err;
+    std::thread creator([&]() {
+        for (int g = 0; g < gpus; ++g) {
+            create_rc[g] = b2pt_create(&ctxs[g], device + g);
+            if (create_rc[g] != B2PT_OK) { create_err = b2pt_last_error(nullptr); return; }
+        }
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{creator};
+
     b2pt_host_scene *scene = demo ? b2pt_host_scene_demo((run_dir + "/../models").c_str(), width, height)
                                   : b2pt_host_scene_from_conf(conf.c_str(), run_dir.c_str(), fix);
     if (!scene) { std::fprintf(stderr, "scene assembly failed: %s\n", b2pt_host_last_error()); return 1; }
@@ -99,9 +113,9 @@ int main(int argc, char **argv) {
     std::printf(" - Generating BVH...\n\n");  // Scene::buildBVH, src/Scene.cpp:15
     if (b2pt_host_scene_build(scene) != 0) { std::fprintf(stderr, "BVH build failed: %s\n", b2pt_host_last_error()); return 1; }
 
-    std::vector<b2pt_ctx *> ctxs(gpus, nullptr);
+    creator.join();
     for (int g = 0; g < gpus; ++g) {
-        if (b2pt_create(&ctxs[g], device + g) != B2PT_OK) { std::fprintf(stderr, "b2pt_create: %s\n", b2pt_last_error(nullptr)); return 1; }
+        if (create_rc[g] != B2PT_OK || !ctxs[g]) { std::fprintf(stderr, "b2pt_create: %s\n", create_err.c_str()); return 1; }
         if (b2pt_upload_scene(ctxs[g], b2pt_host_scene_desc(scene)) != B2PT_OK) { std::fprintf(stderr, "b2pt_upload_scene: %s\n", b2pt_last_error(ctxs[g])); return 1; }
     }
     b2pt_ctx *ctx = ctxs[0];

@@ -144,9 +144,14 @@ enum {
     B2PT_FLAG_FRESH_FRAME = 4,      /* b2pt_render only: out_rgb is OVERWRITTEN with this call's samples (a fresh frame, like the
                                        zero-initialised `framebuffer` of Renderer.cpp:23) instead of accumulated into: the
                                        caller need not zero it and nothing but the camera and parameters goes to the device */
-    B2PT_FLAG_SPLIT_WAVELENGTHS = 2 /* trace the R, G, B paths of a sample as three separate rays from the camera
+    B2PT_FLAG_SPLIT_WAVELENGTHS = 2,/* trace the R, G, B paths of a sample as three separate rays from the camera
                                        on (what the reference does, Renderer.cpp:77-79) instead of sharing rays
                                        while their geometry coincides; same result, used as a self-check          */
+    B2PT_FLAG_INDEPENDENT_WAVELENGTHS = 8 /* three rays AND three sample streams per sample: R, G and B consume independent
+                                       draws like the reference's three castRay calls (Renderer.cpp:77-79).  The default
+                                       (one stream shared by the three paths) has the same per-channel expectation but
+                                       turns chromatic noise into luminance noise — the cross-channel covariance of a
+                                       pixel is not the reference's; this mode restores it at ~3x the ray count.      */
 };
 
 typedef struct b2pt_stats {

@@ -267,6 +267,14 @@ class Ref:
         var = np.maximum(m2.astype(np.float64) - mean.astype(np.float64) ** 2, 0.0)
         return mean, var
 
+    def render_samples_split(self, pixels, sample_begin, sample_count, seed=SEED):
+        """castRay per (pixel, sample, wavelength) on keyed Philox streams with R, G and B reading THREE DIFFERENT streams
+        (tags 0, 2, 3): the oracle of B2PT_FLAG_INDEPENDENT_WAVELENGTHS."""
+        px = i32(pixels)
+        out = np.zeros((len(px), sample_count, 3), np.float32)
+        self.L.ref_render_samples_philox_split(self.h, ip(px), len(px), sample_begin, sample_count, seed & 0xFFFFFFFF, seed >> 32, fp(out))
+        return out
+
     def render_samples_free(self, pixels, sample_count, seed=1, threads=0):
         """Per-sample values [pixels, sample_count, 3] on the reference's own sampling scheme (free-running mt19937 per thread)."""
         px = i32(pixels)

@@ -109,3 +109,41 @@ def test_gpu_frame_matches_the_free_running_reference(which):
     ctx.close()
     ref.close()
     sc.close()
+
+
+def noise_correlation(samples):
+    """Mean over pixels of the correlation between the R and G per-sample values (pixels with variance in both)."""
+    x = samples.astype(np.float64)
+    r, g = x[:, :, 0] - x[:, :, 0].mean(1, keepdims=True), x[:, :, 1] - x[:, :, 1].mean(1, keepdims=True)
+    sr, sg = np.sqrt((r * r).mean(1)), np.sqrt((g * g).mean(1))
+    ok = (sr > 1e-6) & (sg > 1e-6)
+    return float(((r * g).mean(1)[ok] / (sr[ok] * sg[ok])).mean())
+
+
+@pytest.mark.gpu
+def test_independent_wavelength_mode_restores_the_reference_covariance():
+    """B2PT_FLAG_INDEPENDENT_WAVELENGTHS: R, G and B read their own streams.  (i) per sample it equals the oracle's replay with three
+    streams; (ii) its chromatic noise is the reference's: the R-G correlation of the per-sample values matches the free-running
+    reference's, where the default (shared stream) is far more correlated; (iii) it is statistically equivalent like the default."""
+    sc, env = scenes.cornell(64, 64)
+    ref = S.Ref(sc, env)
+    ctx = b2pt.Context(0)
+    ctx.upload(sc)
+    cam = sc.camera
+    px = np.arange(cam.width * cam.height, dtype=np.int32)
+    n = 128
+    indep, st_i = ctx.render_samples(cam, px, 0, n, flags=b2pt.FLAG_INDEPENDENT_WAVELENGTHS)
+    shared, st_s = ctx.render_samples(cam, px, 0, n)
+    want = ref.render_samples_split(px, 0, n)
+    ok = np.abs(indep - want) <= 1e-5 + 2e-4 * np.maximum(np.abs(indep), np.abs(want))
+    assert ok.mean() >= 0.999, ok.mean()
+    assert np.array_equal(indep[:, :, 0], shared[:, :, 0])  # R keeps stream tag 0: the same path either way
+    assert st_i.rays_traced_closest > 2.0 * st_s.rays_traced_closest
+    free = ref.render_samples_free(px, n, seed=5)
+    c_free, c_indep, c_shared = noise_correlation(free), noise_correlation(indep), noise_correlation(shared)
+    assert abs(c_indep - c_free) < 0.03, (c_indep, c_free)
+    assert c_shared > c_free + 0.2, (c_shared, c_free)
+    assert_equivalent(compare(indep, free), "cornell independent wavelengths")
+    ctx.close()
+    ref.close()
+    sc.close()
