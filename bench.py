@@ -325,7 +325,9 @@ def run_single_process(args):
         rays += st.rays_reference; traced += st.rays_traced_closest + st.rays_traced_shadow; launches += st.kernel_launches
     clocks = sampler.summary()
     ref, _ = ctxs[0].render(cam, spp, seed=SEED + args.warmup + args.steps - 1)
-    diff = float(np.abs(ref - out).max())
+    fin = ~(np.isnan(ref) | np.isnan(out))  # NaN samples poison their pixel in the reference too: same pixels on both sides
+    diff = float(np.abs(ref - out)[fin].max())
+    nan_mismatches = int((np.isnan(ref) ^ np.isnan(out)).sum())
     pix = cam.width * cam.height
     K = args.steps
     val = rays / (ms * 1e-3) / 1e6
@@ -334,7 +336,7 @@ def run_single_process(args):
             "config": {"workload": workload_name(args), "frame_spp": spp, "parallelism": f"ONE process, {n} contexts, b2pt_group_render: spp split, one ncclReduce (dlopen) per frame",
                        "timing": "host clock around the blocking call (camera + parameters down, frame back up): value == e2e"},
             "spp_per_s": pix * spp * K / (ms * 1e-3), "traced_rays_per_s_M": traced / (ms * 1e-3) / 1e6, "seconds_per_frame": ms / K / 1e3,
-            "multi_gpu_max_abs_diff": diff, "frame_mean": float(out.mean()),
+            "multi_gpu_max_abs_diff": diff, "multi_gpu_check": {"nan_values": int(np.isnan(out).sum()), "nan_mismatches": nan_mismatches}, "frame_mean": float(out[fin].mean()),
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes_sizeof_inputs(b2pt), "d2h_bytes_per_step": pix * 12, "ms_per_step": ms / K},
             "gpu_launches": int(launches), "clocks": clocks}
     emit(line)
@@ -439,8 +441,13 @@ def run_ours(args):
             fb.zero_()
             ctx.render_device(cam, spp_frame, fb.data_ptr(), sample_begin=0, sample_count=spp_frame, seed=SEED + last_seed_step, max_wave_bundles=args.queue)
             torch.cuda.synchronize(dev)
-            d = (fb - multi_fb).abs()
-            multi = {"max_abs_diff": float(d.max()), "mean_abs_diff": float(d.mean()), "frame_mean": float(fb.mean()),
+            # a sample that evaluates to NaN poisons its pixel in the reference too (framebuffer += NaN, Renderer.cpp:80; the tone map
+            # sends it to 255): such pixels must be the SAME pixels on both sides, the others are compared numerically
+            nan_a, nan_b = torch.isnan(fb), torch.isnan(multi_fb)
+            fin = ~(nan_a | nan_b)
+            d = (fb - multi_fb).abs()[fin]
+            multi = {"max_abs_diff": float(d.max()), "mean_abs_diff": float(d.mean()), "frame_mean": float(fb[fin].mean()),
+                     "nan_values": int(nan_a.sum()), "nan_mismatches": int((nan_a ^ nan_b).sum()),
                      "how": f"rank 0 alone renders the {spp_frame} samples of the last timed frame (same seed) and compares with the {world}-rank reduce; "
                             "differences are float summation order (atomic adds, reduce tree)"}
         barrier()
