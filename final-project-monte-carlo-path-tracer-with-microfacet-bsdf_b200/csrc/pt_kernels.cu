@@ -316,6 +316,28 @@ __global__ void __launch_bounds__(kBlock, B2PT_EXT_MIN_BLOCKS) extend_kernel(Sce
     T.stk = T_stack;
     r.o = r.d = r.inv = mk3(0, 0, 0);
     trav4_begin(T);
+    if (S.n_flat > 0) {
+        // small scene: every lane tests every primitive's leaf record for its own ray (pt::flat_closest) — uniform loop, uniform loads
+        for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+            const float4 o = qo[i], d = qd[i];
+            r = make_ray(xyz(o), xyz(d));
+            refs += (unsigned)__popc((qinfo[i] >> INFO_MASK_SHIFT) & 7u);
+            Hit h;
+            if (ray_needs_reference_tree(r)) binary_walk<COUNT>(S, r, &h, &st);
+            else h = flat_closest<COUNT>(S, r, &st);
+            hit_prim[i] = h.prim;
+            hit_t[i] = (float)h.t;
+            if (hit_t64) hit_t64[i] = h.t;
+        }
+        refs = warp_sum(refs);
+        unsigned long long nodes = st.nodes, prims = st.prims;
+        if (COUNT) { nodes = warp_sum(nodes); prims = warp_sum(prims); }
+        if (lane == 0) {
+            if (refs) atomicAdd(&cnt->rays_reference, refs);
+            if (COUNT && nodes) { atomicAdd(&cnt->nodes, nodes); atomicAdd(&cnt->prims, prims); }
+        }
+        return;
+    }
     Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
@@ -606,6 +628,24 @@ __global__ void __launch_bounds__(kBlock, B2PT_TRAV_MIN_BLOCKS) shadow_kernel(Sc
     T.stk = T_stack;
     r.o = r.d = r.inv = mk3(0, 0, 0);
     shadow_begin(S, r, T, 0.f);
+    if (S.n_flat > 0) {
+        // small scene: the occluder search as one uniform loop over the leaf records (pt::flat_unoccluded); the rare rays that still
+        // need the window search by traversal, or the reference's own topology, take the binary walk
+        for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+            const float4 o = sh_o[i], d = sh_d[i];
+            r = make_ray(xyz(o), xyz(d));
+            const uint32_t tag = __float_as_uint(d.w);
+            bool visible;
+            if ((tag & 0x80000000u) || ray_needs_reference_tree(r)) visible = binary_visible<COUNT>(S, r, o.w, (tag & 0x80000000u) ? 1 : 2, &st);
+            else visible = flat_unoccluded<COUNT>(S, r, o.w, &st);
+            vis[tag & 0x7FFFFFFFu] = visible ? 1 : 0;
+        }
+        if (COUNT) {
+            unsigned long long nodes = warp_sum((unsigned long long)st.nodes), prims = warp_sum((unsigned long long)st.prims);
+            if (lane == 0 && nodes) { atomicAdd(&cnt->sh_nodes, nodes); atomicAdd(&cnt->sh_prims, prims); }
+        }
+        return;
+    }
     Fetch F = fetch_begin(n);
     for (;;) {
         if (!exhausted) {
@@ -1597,7 +1637,7 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     free_scene(ctx);
     PackedScene packed;
     pack_scene(d, packed);
-    ctx->scene_bufs.resize(24);
+    ctx->scene_bufs.resize(25);
     auto up = [&](int slot, const void *src, size_t bytes) -> void * {
         if (upload(ctx, ctx->scene_bufs[slot], src, bytes)) return nullptr;
         return ctx->scene_bufs[slot].p;
@@ -1629,6 +1669,9 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     UP(lt_cnt, const int *, 21, packed.lt_cnt.data(), 4 * packed.lt_cnt.size());
     UP(tri, const float4 *, 22, packed.tri.data(), 16 * packed.tri.size());
     if (!packed.quads.nodes.empty()) UP(nodes4, const float4 *, 23, packed.quads.nodes.data(), sizeof(b2pt_node) * packed.quads.nodes.size());
+    ctx->scene_bufs.resize(25);
+    if (!packed.flat.empty() && !getenv("B2PT_NO_FLAT")) UP(flat, const float4 *, 24, packed.flat.data(), 16 * packed.flat.size());
+    v.n_flat = v.flat ? (int)(packed.flat.size() / 5) : 0;
 #undef UP
     if (!ok) return B2PT_ERR_CUDA;
     v.n_lights = (int)d->n_lights;

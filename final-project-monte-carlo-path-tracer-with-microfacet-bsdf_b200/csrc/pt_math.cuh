@@ -211,6 +211,9 @@ struct SceneView {
                               // (bmin, a) (bmax, kind); EMPTY nodes carry NaN boxes, which fail the box test by themselves
     const float4 *nodes4;     // `nodes` collapsed four-wide (pt_build.hpp): 8 float4 per quad = one 128-byte line per step; null when the
                               // collapse needs a deeper stack than kStackSize4 (then every ray takes the binary walk)
+    const float4 *flat;       // small scenes only (n_flat > 0): per primitive 5 float4 — its exact reference leaf box (bmin | prim id,
+                              // bmax | kind) and (v0, e1, e2) — in primitive-id order, for the walk that simply tests them all
+    int n_flat;               // number of such records (0: the scene is walked through the trees)
     const float4 *nodes_ref;  // the reference's own topology (src/BVH.cpp:27-93), same layout: used by rays whose slab
                               // products can be NaN (see ray_needs_reference_tree) and by the parity entry points
     const float4 *v0, *e1, *e2, *nrm;  // per primitive
@@ -532,6 +535,72 @@ PT_HD Hit closest_hit4(const SceneView &S, const Ray &r, TravStats *st) {
     trav4_begin(T);
     while (trav4_step<COUNT>(S, r, T, st)) {}
     return T.h;
+}
+
+// ---- small scenes: no tree at all ------------------------------------------------------------------------------------------
+// The reference tests a primitive iff its own leaf box passes Bounds3::IntersectP (pt_build.hpp), so for a scene of a few dozen
+// primitives (the Cornell box: 32 triangles + 3 spheres, BASELINE configs[0] and [4]) the cheapest exact walk is no walk: every
+// lane runs the same loop over the same records (uniform addresses: one L1 wavefront per load for the whole warp, no stack, no
+// divergence except the primitive test itself), tests the leaf box with the reference's arithmetic and the primitive when it
+// passes.  Ascending primitive id + "<=" keeps the reference's tie rule (later leaf wins).  Rays whose slab products can be
+// NaN are excluded by the callers as for the trees (their box tests depend on the ancestors' boxes too).
+constexpr int kFlatMax = 64;
+template <bool COUNT>
+PT_HD Hit flat_closest(const SceneView &S, const Ray &r, TravStats *st) {
+    Hit h;
+    h.t = 1.7976931348623157e308;
+    h.prim = -1;
+    float bound = INFINITY;
+    for (int i = 0; i < S.n_flat; ++i) {
+        const float4 *q = S.flat + 5 * (size_t)i;
+        const float4 lo = PT_LDG4(q), hi = PT_LDG4(q + 1);
+        float tl;
+        if (COUNT) st->nodes++;
+        if (!box_hit(xyz(lo), xyz(hi), r, &tl) || tl > bound) continue;
+        const float4 a = PT_LDG4(q + 2), b = PT_LDG4(q + 3);
+        double t;
+        bool ok;
+        if (COUNT) st->prims++;
+        if (f2u(hi.w) == NODE_TRIANGLE) {
+            const float4 c = PT_LDG4(q + 4);
+            double u, v;
+            ok = tri_hit(xyz(a), xyz(b), xyz(c), r, &t, &u, &v);
+        } else {
+            float tf;
+            ok = sphere_hit(xyz(a), b.x, r, &tf);
+            t = (double)tf;
+        }
+        if (ok && t <= h.t) { h.t = t; h.prim = (int)f2u(lo.w); bound = prune_bound(t); }
+    }
+    return h;
+}
+// The occluder search (phase 2 of the visibility decision): any hit with t < dist outside the window?
+template <bool COUNT>
+PT_HD bool flat_unoccluded(const SceneView &S, const Ray &r, float dist, TravStats *st) {
+    const double eps = (double)kEps, dd = (double)dist;
+    const float hi_t = dist + (4e-3f + 1e-5f * dist);
+    for (int i = 0; i < S.n_flat; ++i) {
+        const float4 *q = S.flat + 5 * (size_t)i;
+        const float4 lo = PT_LDG4(q), hi = PT_LDG4(q + 1);
+        float tl;
+        if (COUNT) st->nodes++;
+        if (!box_hit(xyz(lo), xyz(hi), r, &tl) || tl > hi_t) continue;
+        const float4 a = PT_LDG4(q + 2), b = PT_LDG4(q + 3);
+        double t;
+        bool ok;
+        if (COUNT) st->prims++;
+        if (f2u(hi.w) == NODE_TRIANGLE) {
+            const float4 c = PT_LDG4(q + 4);
+            double u, v;
+            ok = tri_hit(xyz(a), xyz(b), xyz(c), r, &t, &u, &v);
+        } else {
+            float tf;
+            ok = sphere_hit(xyz(a), b.x, r, &tf);
+            t = (double)tf;
+        }
+        if (ok && !(fabs(t - dd) < eps) && t < dd) return false;
+    }
+    return true;
 }
 
 // ---- visibility of a light sample: Scene::directLighting, src/Scene.cpp:72-75 -----------------------------

@@ -28,6 +28,7 @@ struct PackedScene {
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
     // Entry = (bmin, prim id) (bmax, kind): the primitive's own reference leaf box, tested before the primitive.
     std::vector<float4> tri;  // (v0, e1, e2) per primitive, interleaved
+    std::vector<float4> flat; // small scenes (<= pt::kFlatMax primitives): per primitive (leaf bmin | id, leaf bmax | kind, v0, e1, e2)
     std::vector<float4> lt_entries;
     std::vector<int> lt_off, lt_cnt;  // cnt < 0: too many neighbours, the window is searched by traversal instead
 };
@@ -105,6 +106,33 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
         std::memcpy(&out.tri[3 * i], d->prim_v0 + 4 * i, 16);
         std::memcpy(&out.tri[3 * i + 1], d->prim_e1 + 4 * i, 16);
         std::memcpy(&out.tri[3 * i + 2], d->prim_e2 + 4 * i, 16);
+    }
+    out.flat.clear();
+    if (d->n_prims <= (uint32_t)kFlatMax) {
+        // every primitive must own exactly one leaf (its box is what decides whether the reference tests it)
+        std::vector<int> owner(d->n_prims, -1);
+        bool ok = true;
+        for (uint32_t i = 0; i < d->n_nodes; ++i) {
+            const b2pt_node &n = d->nodes[i];
+            if (n.kind != B2PT_NODE_TRIANGLE && n.kind != B2PT_NODE_SPHERE) continue;
+            if (owner[n.a] >= 0) ok = false;
+            owner[n.a] = (int)i;
+        }
+        for (uint32_t p = 0; p < d->n_prims; ++p) ok = ok && owner[p] >= 0;
+        if (ok) {
+            out.flat.resize(5 * (size_t)d->n_prims);
+            for (uint32_t p = 0; p < d->n_prims; ++p) {
+                const b2pt_node &n = d->nodes[owner[p]];
+                float4 lo = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], 0.f), hi = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], 0.f);
+                const uint32_t kind = n.kind;
+                std::memcpy(&lo.w, &p, 4);
+                std::memcpy(&hi.w, &kind, 4);
+                out.flat[5 * (size_t)p] = lo; out.flat[5 * (size_t)p + 1] = hi;
+                std::memcpy(&out.flat[5 * (size_t)p + 2], d->prim_v0 + 4 * (size_t)p, 16);
+                std::memcpy(&out.flat[5 * (size_t)p + 3], d->prim_e1 + 4 * (size_t)p, 16);
+                std::memcpy(&out.flat[5 * (size_t)p + 4], d->prim_e2 + 4 * (size_t)p, 16);
+            }
+        }
     }
     out.nodes_ref.assign(d->nodes, d->nodes + d->n_nodes);
     for (auto &n : out.nodes_ref)

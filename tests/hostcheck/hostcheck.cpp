@@ -57,6 +57,8 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     v.n_lights = (int)d->n_lights; v.light_area = h->light_area.data(); v.light_root = h->light_root.data(); v.light_mat = h->light_mat.data();
     v.ln_area = h->ln_area.data(); v.ln_left = h->ln_left.data(); v.ln_right = h->ln_right.data(); v.ln_prim = h->ln_prim.data();
     v.tri = h->packed.tri.data();
+    v.flat = h->packed.flat.empty() ? nullptr : h->packed.flat.data();
+    v.n_flat = (int)(h->packed.flat.size() / 5);
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     for (int k = 0; k < 3; ++k) v.light_c[k] = h->packed.light_sphere[k];
     v.light_r = h->packed.light_sphere[3];
@@ -411,4 +413,37 @@ long hc_check_eval3(void *h, int mat, const float *wi, const float *wo, const fl
     return bad;
 }
 float hc_u01(unsigned word) { return unit_from_word(word); }
+// the treeless walks of small scenes (pt::flat_closest / flat_unoccluded); returns 0 when the scene has no flat records
+int hc_flat_intersect(void *h, const float *o, const float *d, long n, int *prim, double *t) {
+    const SceneView &S = ((HcScene *)h)->view;
+    if (S.n_flat <= 0) return 0;
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        const Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
+        const Hit hit = ray_needs_reference_tree(r) ? closest_hit<false>(S, r, &st) : flat_closest<false>(S, r, &st);
+        prim[i] = hit.prim; t[i] = hit.t;
+    }
+    return 1;
+}
+// visibility decision with the occluder search done by the flat walk (window witness from a traversal, like light_visible)
+int hc_flat_shadow(void *h, const float *o, const float *d, const float *dist, long n, int *visible) {
+    const SceneView &S = ((HcScene *)h)->view;
+    if (S.n_flat <= 0) return 0;
+    for (long i = 0; i < n; ++i) {
+        TravStats st{0, 0};
+        const Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
+        if (ray_needs_reference_tree(r)) { visible[i] = light_visible<false>(S, r, dist[i], &st) ? 1 : 0; continue; }
+        // phase 1 (is there a hit inside the window?) by the binary walk, phase 2 (no closer hit outside it?) by the flat walk
+        ShadowTrav T;
+        uint32_t stack[kStackSize];
+        T.stk = stack;
+        shadow_begin(S, r, T, dist[i], 1);
+        bool witness = false;
+        while (shadow_step<false>(S, r, dist[i], T, &st)) {
+            if (T.phase == 2) { witness = true; break; }
+        }
+        visible[i] = (witness && flat_unoccluded<false>(S, r, dist[i], &st)) ? 1 : 0;
+    }
+    return 1;
+}
 }

@@ -104,6 +104,22 @@ class HostCheck:
         self.L.hc_shadow4(self.h, fp(o), fp(d), fp(s), C.c_long(len(o)), ip(vis), cnt)
         return (vis, (cnt[0], cnt[1])) if counts else vis
 
+    def flat_intersect(self, o, d):
+        """Closest hits by the treeless walk of small scenes (pt::flat_closest); None when the scene is not small."""
+        o, d = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
+        prim = np.zeros(len(o), np.int32)
+        t = np.zeros(len(o), np.float64)
+        if not self.L.hc_flat_intersect(self.h, fp(o), fp(d), C.c_long(len(o)), ip(prim), t.ctypes.data_as(c_double_p)):
+            return None
+        return prim, t
+
+    def flat_shadow(self, o, d, dist):
+        o, d, s = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3), f32(dist)
+        vis = np.zeros(len(o), np.int32)
+        if not self.L.hc_flat_shadow(self.h, fp(o), fp(d), fp(s), C.c_long(len(o)), ip(vis)):
+            return None
+        return vis
+
     def shadow_with_light_node(self, o, d, dist, light_prim):
         o, d, s, lp = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3), f32(dist), i32(light_prim)
         vis = np.zeros(len(o), np.int32)

@@ -114,6 +114,30 @@ def test_textured_uv(world):
     assert np.array_equal(uv_h[on_floor].view(np.uint32), uv_r[on_floor].view(np.uint32))
 
 
+def test_treeless_walk_of_small_scenes(world):
+    """Scenes of at most pt::kFlatMax primitives (the Cornell box) are not walked through a tree at all: every primitive's own leaf
+    box is tested, then the primitive (pt::flat_closest / flat_unoccluded).  Same hits, same t bits, same visibility decisions."""
+    name, sc, ref, hc = world
+    o, d, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=2000, samples=2, seed=6)
+    got = hc.flat_intersect(o, d)
+    if name != "cornell":
+        assert got is None  # the chess scene has 38 458 primitives
+        return
+    prim_r, t_r, *_ = ref.intersect(o, d)
+    assert np.array_equal(got[0], prim_r)
+    hit = prim_r >= 0
+    assert np.array_equal(got[1][hit].view(np.uint64), t_r[hit].view(np.uint64))
+    prim_s, t_s, *_ = ref.intersect(p, ws)
+    want = ((prim_s >= 0) & (np.abs(t_s - dist.astype(np.float64)) < np.float64(np.float32(1e-4)))).astype(np.int32)
+    assert np.array_equal(hc.flat_shadow(p, ws, dist), want)
+    # degenerate rays (zero direction components, origins on box planes) go through the reference's topology: still equal
+    root = sc.desc.nodes[0]
+    od, dd = degenerate_rays(np.random.RandomState(3), list(root.bmin), list(root.bmax), 4000)
+    pr, tr, *_ = ref.intersect(od, dd)
+    g = hc.flat_intersect(od, dd)
+    assert np.array_equal(g[0], pr) and np.array_equal(g[1][pr >= 0].view(np.uint64), tr[pr >= 0].view(np.uint64))
+
+
 def test_shadow_decision(world):
     name, sc, ref, hc = world
     _, _, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=1500, samples=2, seed=4)
