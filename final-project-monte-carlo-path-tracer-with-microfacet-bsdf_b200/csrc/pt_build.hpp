@@ -14,8 +14,11 @@
 // emitted in the same 32-byte sibling-pair layout and depth-first order the kernels already walk.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <thread>
 #include <vector>
 
 #include "b2pt.h"
@@ -73,26 +76,44 @@ struct SahBuilder {
             leaves.push_back(l);
         }
     }
-    int alloc_pair() {
+    // Subtrees below kParDepth are built by worker threads (the builder is the largest host cost of b2pt_upload_scene: 1.1 s for the
+    // 296 k-triangle scene on one thread): the top of the tree is built first and records one task per subtree, each task partitions its
+    // own disjoint range of `leaves` and emits into a private vector, and the vectors are spliced in task order — the result does
+    // not depend on the scheduling.
+    static constexpr int kParDepth = 4;
+    static constexpr size_t kParMinLeaves = 4096;
+    struct Task {
+        int slot;
+        size_t begin, end;
+        int depth;
+    };
+    std::vector<Task> tasks;
+    bool collect_tasks = false;
+
+    static int alloc_pair(std::vector<b2pt_node> &o) {
         b2pt_node e{};
         e.kind = B2PT_NODE_EMPTY;
         for (int k = 0; k < 3; ++k) { e.bmin[k] = NAN; e.bmax[k] = NAN; }  // NaN boxes fail Bounds3::IntersectP by themselves
-        out.push_back(e);
-        out.push_back(e);
-        return (int)out.size() / 2 - 1;
+        o.push_back(e);
+        o.push_back(e);
+        return (int)o.size() / 2 - 1;
     }
     static void set_box(b2pt_node &n, const BuildBox &b) {
         for (int k = 0; k < 3; ++k) { n.bmin[k] = b.mn[k]; n.bmax[k] = b.mx[k]; }
     }
-    // Fills slot `slot` with the subtree over leaves[begin, end).
-    void build(int slot, size_t begin, size_t end, int depth) {
-        max_depth = std::max(max_depth, depth);
+    // Fills slot `slot` of `o` with the subtree over leaves[begin, end); returns the deepest level reached.
+    int build(std::vector<b2pt_node> &o, int slot, size_t begin, size_t end, int depth) {
+        int deepest = depth;
         if (end - begin == 1) {
             const Leaf &l = leaves[begin];
-            set_box(out[slot], l.box);
-            out[slot].kind = l.kind;
-            out[slot].a = l.prim;
-            return;
+            set_box(o[slot], l.box);
+            o[slot].kind = l.kind;
+            o[slot].a = l.prim;
+            return deepest;
+        }
+        if (collect_tasks && depth == kParDepth && end - begin >= kParMinLeaves) {
+            tasks.push_back(Task{slot, begin, end, depth});
+            return deepest;
         }
         BuildBox bounds = box_empty_b(), cb = box_empty_b();
         for (size_t i = begin; i < end; ++i) {
@@ -150,20 +171,50 @@ struct SahBuilder {
             std::nth_element(leaves.begin() + begin, leaves.begin() + mid, leaves.begin() + end,
                              [&](const Leaf &a, const Leaf &b) { return a.c[axis] < b.c[axis]; });
         }
-        int a = alloc_pair();
-        set_box(out[slot], bounds);
-        out[slot].kind = B2PT_NODE_INTERIOR;
-        out[slot].a = (uint32_t)a;
-        build(2 * a, begin, mid, depth + 1);
-        build(2 * a + 1, mid, end, depth + 1);
+        int a = alloc_pair(o);
+        set_box(o[slot], bounds);
+        o[slot].kind = B2PT_NODE_INTERIOR;
+        o[slot].a = (uint32_t)a;
+        deepest = std::max(deepest, build(o, 2 * a, begin, mid, depth + 1));
+        deepest = std::max(deepest, build(o, 2 * a + 1, mid, end, depth + 1));
+        return deepest;
     }
     // Returns the nodes (sibling pairs, root = nodes[0], nodes[1] an EMPTY filler) and the tree depth.
     void run(const b2pt_scene_desc *d) {
         collect(d);
         out.clear();
+        tasks.clear();
         max_depth = 0;
-        alloc_pair();
-        if (!leaves.empty()) build(0, 0, leaves.size(), 0);
+        alloc_pair(out);
+        if (leaves.empty()) return;
+        collect_tasks = leaves.size() >= 4 * kParMinLeaves;
+        max_depth = build(out, 0, 0, leaves.size(), 0);
+        collect_tasks = false;
+        if (tasks.empty()) return;
+        // the recorded subtrees, in parallel; local pair 0 holds the subtree's root in its first slot
+        std::vector<std::vector<b2pt_node>> parts(tasks.size());
+        std::vector<int> depths(tasks.size(), 0);
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (size_t t = next.fetch_add(1); t < tasks.size(); t = next.fetch_add(1)) {
+                alloc_pair(parts[t]);
+                depths[t] = build(parts[t], 0, tasks[t].begin, tasks[t].end, tasks[t].depth);
+            }
+        };
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        for (unsigned i = 1; i < std::min<unsigned>(hw, (unsigned)tasks.size()); ++i) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+        for (size_t t = 0; t < tasks.size(); ++t) {
+            const uint32_t shift = (uint32_t)(out.size() / 2) - 1;  // local pair p (>= 1) becomes pair p + shift
+            std::vector<b2pt_node> &loc = parts[t];
+            for (b2pt_node &n : loc)
+                if (n.kind == B2PT_NODE_INTERIOR) n.a += shift;
+            out[tasks[t].slot] = loc[0];
+            out.insert(out.end(), loc.begin() + 2, loc.end());
+            max_depth = std::max(max_depth, depths[t]);
+        }
     }
 };
 

@@ -17,6 +17,8 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "b2pt_host.h"
@@ -131,6 +133,7 @@ struct b2pt_host_scene {
     std::vector<std::string> mat_names;
     std::vector<b2pt_material> mats;
     std::vector<HostObject> objects;
+    std::map<std::string, MeshData> mesh_cache;  // parsed mesh files by path: one read per distinct file
 
     // camera / renderer / scene options
     int width = 384, height = 384;
@@ -251,10 +254,16 @@ int add_mesh_from_stream(b2pt_host_scene *s, const MeshData &md, const std::stri
 
 int add_mesh_file(b2pt_host_scene *s, const std::string &path, int material, V3 tr, float zoom) {
     if (material < 0 || material >= (int)s->mats.size()) { set_error("bad material index"); return -1; }
-    MeshData md;
-    std::string err;
-    if (!load_mesh_stream(path, md, err)) { set_error(err); return -1; }
-    return add_mesh_from_stream(s, md, path, material, tr, zoom);
+    // every distinct file is read and parsed ONCE per scene (the reference parses low_soldier.obj fourteen times, main.cpp:267-268);
+    // each instance still gets its own translated triangles, as MeshTriangle's constructor makes them
+    auto it = s->mesh_cache.find(path);
+    if (it == s->mesh_cache.end()) {
+        MeshData md;
+        std::string err;
+        if (!load_mesh_stream(path, md, err)) { set_error(err); return -1; }
+        it = s->mesh_cache.emplace(path, std::move(md)).first;
+    }
+    return add_mesh_from_stream(s, it->second, path, material, tr, zoom);
 }
 
 void setup_camera_pod(b2pt_host_scene *s) {
@@ -518,22 +527,40 @@ int b2pt_host_scene_build(b2pt_host_scene *s) {
     s->ln_area.clear(); s->ln_left.clear(); s->ln_right.clear(); s->ln_prim.clear();
 
     // per-mesh trees (Triangle.hpp:128-134), then the scene tree over objects (Scene.cpp:14-17)
+    // The meshes' trees do not depend on each other (the reference builds one per MeshTriangle constructor call): they are built by
+    // a few worker threads — the sorts of the 14 soldiers and the king are most of the host time of the high-poly scene.
     std::vector<std::vector<BuildNode>> mesh_trees(s->objects.size());
     std::vector<BuildItem> top_items;
     for (size_t k = 0; k < s->objects.size(); ++k) {
         HostObject &o = s->objects[k];
-        if (o.kind == 0) {
-            if (o.tris.empty()) { set_error("mesh without triangles"); return -1; }
-            std::vector<BuildItem> items;
-            std::vector<int> ids;
-            for (size_t i = 0; i < o.tris.size(); ++i) {
-                items.push_back(BuildItem{tri_box(o.tris[i]), o.tris[i].area});
-                ids.push_back((int)i);
-            }
-            recursive_build(items, ids, mesh_trees[k]);
-            o.face_to_prim.assign(o.tris.size(), -1);
-        }
+        if (o.kind == 0 && o.tris.empty()) { set_error("mesh without triangles"); return -1; }
         top_items.push_back(BuildItem{o.bbox, o.area});
+    }
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (size_t k = next.fetch_add(1); k < s->objects.size(); k = next.fetch_add(1)) {
+                HostObject &o = s->objects[k];
+                if (o.kind != 0) continue;
+                std::vector<BuildItem> items;
+                std::vector<int> ids;
+                items.reserve(o.tris.size()); ids.reserve(o.tris.size());
+                for (size_t i = 0; i < o.tris.size(); ++i) {
+                    items.push_back(BuildItem{tri_box(o.tris[i]), o.tris[i].area});
+                    ids.push_back((int)i);
+                }
+                recursive_build(items, ids, mesh_trees[k]);
+                o.face_to_prim.assign(o.tris.size(), -1);
+            }
+        };
+        size_t total_tris = 0;
+        for (const HostObject &o : s->objects) total_tris += o.tris.size();
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n_workers = total_tris < 20000 ? 1u : std::min<unsigned>(hw, (unsigned)s->objects.size());
+        std::vector<std::thread> pool;
+        for (unsigned i = 1; i < n_workers; ++i) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
     }
     std::vector<BuildNode> top;
     {
