@@ -78,7 +78,7 @@ struct Counters {
     unsigned int n_cur, n_next, n_shadow, n_vis;  // n_shadow: shadow rays queued for traversal; n_vis: visibility slots handed out
     unsigned int n_class[12];
     unsigned int fetch_extend, fetch_shadow;  // dynamic-fetch cursors of the traversal kernels
-    unsigned int n_lit, pad1;                 // accepted light samples of this bounce
+    unsigned int n_lit, fetch_shaft;          // accepted light samples of this bounce; cursor of shaft_kernel
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
     unsigned long long listed;  // light samples decided from their vertex's candidate list (no traversal)
     unsigned int max_depth, pad2;
@@ -503,15 +503,18 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
     const unsigned ndir = (unsigned)S.n_dir;
     unsigned listed = 0;
+    __shared__ float4 s_rec[kWarps][5 * kShaftK];  // the list of the warp's current vertex, fetched once: leaf box | prim | kind, primitive record
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
         const unsigned i = it + threadIdx.x;
-        bool queue = false;
+        bool queue = false, from_list = false;
         int w = 0;
+        unsigned v = 0;
         f3 pn = mk3(0, 0, 0);
         NeeGeom g;
         g.ws = mk3(0, 0, 1); g.dist = 0.f;
         if (i < n) {
-            const unsigned v = i / ndir, k = i - v * ndir;
+            v = i / ndir;
+            const unsigned k = i - v * ndir;
             const float4 a = vtx_pn[v];
             const uint2 ps = vtx_ps[v];
             pn = xyz(a);
@@ -547,11 +550,36 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
                     // a vertex with a candidate list: its samples test exactly the listed primitives (pt::list_visible), all
                     // lanes of a vertex reading the same records; rays that need the reference's topology walk it as before
                     const unsigned lc = vtx_lcnt ? vtx_lcnt[v] : kShaftNone;
-                    if (lc != kShaftNone && !ray_needs_reference_tree(sr)) {
-                        vis[i] = list_visible(S, vtx_list + (size_t)v * kShaftK, (int)lc, sr, g.dist, w == 1) ? 1 : 0;
-                        ++listed;
-                    } else queue = true;
+                    if (lc != kShaftNone && !ray_needs_reference_tree(sr)) from_list = true;
+                    else queue = true;
                 }
+            }
+        }
+        if (vtx_lcnt) {
+            // The lanes of a vertex (all 32 when n_dir is 32) test the same list: the warp fetches it once, lane j the j-th entry
+            // (leaf, then its primitive: every load of the list in flight together), and each sample reads the records from shared memory.
+            const unsigned lane = threadIdx.x & 31u;
+            float4 *rec = s_rec[threadIdx.x >> 5];
+            unsigned pending = __ballot_sync(0xffffffffu, from_list);
+            while (pending) {
+                const unsigned vv = __shfl_sync(0xffffffffu, v, __ffs(pending) - 1);
+                const unsigned cntv = vtx_lcnt[vv];
+                if (lane < cntv) {
+                    const uint32_t ref = vtx_list[(size_t)vv * kShaftK + lane];
+                    const float4 *qn = S.nodes + 4 * (size_t)(ref >> 1) + 2 * (ref & 1u);
+                    const float4 a = PT_LDG4(qn), b = PT_LDG4(qn + 1);
+                    const float4 *qt = S.tri + 3 * (size_t)f2u(a.w);
+                    rec[5 * lane] = a; rec[5 * lane + 1] = b;
+                    rec[5 * lane + 2] = PT_LDG4(qt); rec[5 * lane + 3] = PT_LDG4(qt + 1); rec[5 * lane + 4] = PT_LDG4(qt + 2);
+                }
+                __syncwarp();
+                const bool mine = from_list && v == vv;
+                if (mine) {
+                    vis[i] = list_visible_records(rec, (int)cntv, make_ray(pn, g.ws), g.dist, w == 1) ? 1 : 0;
+                    ++listed;
+                }
+                __syncwarp();
+                pending &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
         const unsigned qx = block_alloc(queue ? 1u : 0u, &cnt->n_shadow);
@@ -567,14 +595,42 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
     }
 }
 
-// ---- shaft: the candidate list of every shaded vertex (pt::shaft_collect), one lane per vertex ---------------------------------
-__global__ void __launch_bounds__(kBlock) shaft_kernel(SceneView S, const float4 *__restrict__ vtx_pn, const unsigned *__restrict__ n_vis_ptr,
-                                                       uint32_t *__restrict__ vtx_list, unsigned char *__restrict__ vtx_lcnt) {
+// ---- shaft: the candidate list of every shaded vertex (pt::shaft_step), persistent warps with dynamic fetch like extend -------------
+__global__ void __launch_bounds__(kBlock, 8) shaft_kernel(SceneView S, const float4 *__restrict__ vtx_pn, const unsigned *__restrict__ n_vis_ptr,
+                                                          unsigned *__restrict__ next, uint32_t *__restrict__ vtx_list, unsigned char *__restrict__ vtx_lcnt) {
     const unsigned nv = *n_vis_ptr / (unsigned)S.n_dir;
-    uint32_t stk[kStackSize];
-    for (unsigned v = blockIdx.x * kBlock + threadIdx.x; v < nv; v += gridDim.x * kBlock) {
-        const int n = shaft_collect(S, xyz(vtx_pn[v]), vtx_list + (size_t)v * kShaftK, stk);
-        vtx_lcnt[v] = (unsigned char)(n < 0 ? kShaftNone : (unsigned)n);
+    const unsigned lane = threadIdx.x & 31u;
+    bool has = false, exhausted = false;
+    unsigned v = 0;
+    ShaftTrav T;
+    uint32_t T_stack[kStackSize];
+    T.stk = T_stack;
+    T.out = vtx_list;
+    shaft_begin(S, mk3(0, 0, 0), T);
+    Fetch F = fetch_begin(nv);
+    for (;;) {
+        if (!exhausted) {
+            const unsigned got = fetch_rays(F, !has, nv, next, lane);
+            if (!has && got != 0xFFFFFFFFu) {
+                v = got;
+                T.out = vtx_list + (size_t)v * kShaftK;
+                if (shaft_begin(S, xyz(vtx_pn[v]), T)) has = true;
+                else vtx_lcnt[v] = (unsigned char)kShaftNone;
+            }
+            exhausted = F.dry && F.lo >= F.hi;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!act) {
+            if (exhausted) break;
+            continue;
+        }
+        do {
+            if (has && !shaft_step(S, T)) {
+                vtx_lcnt[v] = (unsigned char)(T.n < 0 ? kShaftNone : (unsigned)T.n);
+                has = false;
+            }
+            act = __ballot_sync(0xffffffffu, has);
+        } while (act && (exhausted || __popc(act) > kRefillBelow));
     }
 }
 
@@ -1054,6 +1110,7 @@ __global__ void swap_counts_kernel(Counters *cnt) {
     for (int c = 0; c < kClasses; ++c) cnt->n_class[c] = 0;
     cnt->fetch_extend = 0;
     cnt->fetch_shadow = 0;
+    cnt->fetch_shaft = 0;
     cnt->n_lit = 0;
     plan_generation(cnt);
 }
@@ -1452,7 +1509,7 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         }
         if (S.enable_shadow) {
             if (lists) {
-                shaft_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, &dc->n_vis, ctx->wb.vtx_list, ctx->wb.vtx_lcnt);
+                shaft_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, &dc->n_vis, &dc->fetch_shaft, ctx->wb.vtx_list, ctx->wb.vtx_lcnt);
                 launches++;
             }
             nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, qa, ctx->wb.vtx_pn, ctx->wb.vtx_ps, ctx->wb.vtx_ray, ctx->wb.hit_prim,

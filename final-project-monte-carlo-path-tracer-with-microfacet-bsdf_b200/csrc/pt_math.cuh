@@ -351,12 +351,9 @@ PT_HD float prune_bound(double best) {
 }
 
 // primitive test of a leaf: Triangle::getIntersection or Sphere::getIntersection
-PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
-    const float4 *q = S.tri + 3 * (size_t)prim;
-    float4 a = PT_LDG4(q);
-    float4 b = PT_LDG4(q + 1);
+// ... from the primitive's interleaved record (S.tri: v0, e1, e2 | centre, radius)
+PT_HD bool prim_hit_record(float4 a, float4 b, float4 c, uint32_t kind, const Ray &r, double *t) {
     if (kind == NODE_TRIANGLE) {
-        float4 c = PT_LDG4(q + 2);
         double u, v;
         return tri_hit(xyz(a), xyz(b), xyz(c), r, t, &u, &v);
     }
@@ -364,6 +361,14 @@ PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray 
     bool ok = sphere_hit(xyz(a), b.x, r, &tf);
     *t = (double)tf;
     return ok;
+}
+PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
+    const float4 *q = S.tri + 3 * (size_t)prim;
+    float4 a = PT_LDG4(q);
+    float4 b = PT_LDG4(q + 1);
+    float4 c = b;
+    if (kind == NODE_TRIANGLE) c = PT_LDG4(q + 2);
+    return prim_hit_record(a, b, c, kind, r, t);
 }
 
 // The traversal tree may be any tree over the reference's leaf boxes (pt_build.hpp explains why the hits are the same)
@@ -726,7 +731,10 @@ PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats
 #endif
 constexpr int kShaftK = B2PT_SHAFT_K;     // longest list kept; a longer one means "walk the tree as before"
 constexpr uint32_t kShaftNone = 0xFFu;    // stored count of a vertex without a list
-constexpr int kShaftMaxSteps = 192;       // sibling pairs a collection may visit before it gives up
+#ifndef B2PT_SHAFT_MAX_STEPS
+#define B2PT_SHAFT_MAX_STEPS 192
+#endif
+constexpr int kShaftMaxSteps = B2PT_SHAFT_MAX_STEPS;  // sibling pairs a collection may visit before it gives up
 struct Cone {
     f3 p, dlo, dhi, rlo, rhi;  // apex, (L.min - p, L.max - p) and their reciprocals
     float m;
@@ -767,31 +775,53 @@ PT_HD bool cone_meets_box(const Cone &c, f3 bmin, f3 bmax) {
     // rounding of the six products when s is large (boxes far behind the lights)
     return ok && !(slo > shi * 1.00001f + 1e-6f);
 }
-// Leaves (as 2 * pair + side of S.nodes) whose box meets the cone of vertex p; returns their number, or -1 when there are more
-// than kShaftK, the walk is too long, or the scene has no usable light box.  stk: kStackSize entries.
-PT_HD int shaft_collect(const SceneView &S, f3 p, uint32_t *out, uint32_t *stk, int *steps_out = nullptr) {
-    const Cone c = cone_make(S, p);
-    if (!c.ok) return -1;
-    int n = 0, sp = 0, steps = 0;
-    uint32_t pair = 0;
-    for (;;) {
-        if (steps_out) *steps_out = steps;
-        if (++steps > kShaftMaxSteps) return -1;
-        const float4 *q = S.nodes + 4 * (size_t)pair;
-        const float4 l0 = PT_LDG4(q), l1 = PT_LDG4(q + 1), r0 = PT_LDG4(q + 2), r1 = PT_LDG4(q + 3);
-        const uint32_t lk = f2u(l1.w), rk = f2u(r1.w);
-        // EMPTY fillers carry NaN boxes: every comparison above is false for them, which would read as "meets"
-        const bool hl = lk != NODE_EMPTY && cone_meets_box(c, xyz(l0), xyz(l1));
-        const bool hr = rk != NODE_EMPTY && cone_meets_box(c, xyz(r0), xyz(r1));
-        if (hl && lk != NODE_INTERIOR) { if (n == kShaftK) return -1; out[n++] = 2u * pair; }
-        if (hr && rk != NODE_INTERIOR) { if (n == kShaftK) return -1; out[n++] = 2u * pair + 1u; }
-        const bool il = hl && lk == NODE_INTERIOR, ir = hr && rk == NODE_INTERIOR;
-        if (il && ir) { if (sp >= kStackSize) return -1; stk[sp++] = f2u(r0.w); pair = f2u(l0.w); }
-        else if (il) pair = f2u(l0.w);
-        else if (ir) pair = f2u(r0.w);
-        else if (sp > 0) pair = stk[--sp];
-        else return n;
+// Leaves (as 2 * pair + side of S.nodes) whose box meets the cone of a vertex, one sibling pair per step so that the kernel can
+// refill finished lanes (pt_kernels.cu shaft_kernel).  T.n ends as the number of leaves, or -1 when there are more than kShaftK,
+// the walk is too long, or the scene has no usable light box.  stk: kStackSize entries, out: kShaftK entries.
+struct ShaftTrav {
+    Cone c;
+    uint32_t pair;
+    int n, sp, steps;
+    uint32_t *stk, *out;
+};
+PT_HD bool shaft_begin(const SceneView &S, f3 p, ShaftTrav &T) {
+    T.c = cone_make(S, p);
+    T.pair = 0; T.n = 0; T.sp = 0; T.steps = 0;
+    if (!T.c.ok) { T.n = -1; return false; }
+    return true;
+}
+// Returns false when the collection has finished (T.n).
+PT_HD bool shaft_step(const SceneView &S, ShaftTrav &T) {
+    if (++T.steps > kShaftMaxSteps) { T.n = -1; return false; }
+    const float4 *q = S.nodes + 4 * (size_t)T.pair;
+    const float4 l0 = PT_LDG4(q), l1 = PT_LDG4(q + 1), r0 = PT_LDG4(q + 2), r1 = PT_LDG4(q + 3);
+    const uint32_t lk = f2u(l1.w), rk = f2u(r1.w);
+    // EMPTY fillers carry NaN boxes: every comparison of the cone test is false for them, which would read as "meets"
+    const bool hl = lk != NODE_EMPTY && cone_meets_box(T.c, xyz(l0), xyz(l1));
+    const bool hr = rk != NODE_EMPTY && cone_meets_box(T.c, xyz(r0), xyz(r1));
+    const bool ll = hl && lk != NODE_INTERIOR, rl = hr && rk != NODE_INTERIOR;
+    if (T.n + (ll ? 1 : 0) + (rl ? 1 : 0) > kShaftK) { T.n = -1; return false; }
+    if (ll) T.out[T.n++] = 2u * T.pair;
+    if (rl) T.out[T.n++] = 2u * T.pair + 1u;
+    const bool il = hl && lk == NODE_INTERIOR, ir = hr && rk == NODE_INTERIOR;
+    if (il && ir) {
+        if (T.sp >= kStackSize) { T.n = -1; return false; }
+        T.stk[T.sp++] = f2u(r0.w);
+        T.pair = f2u(l0.w);
+        return true;
     }
+    if (il) { T.pair = f2u(l0.w); return true; }
+    if (ir) { T.pair = f2u(r0.w); return true; }
+    if (T.sp > 0) { T.pair = T.stk[--T.sp]; return true; }
+    return false;
+}
+PT_HD int shaft_collect(const SceneView &S, f3 p, uint32_t *out, uint32_t *stk, int *steps_out = nullptr) {
+    ShaftTrav T;
+    T.stk = stk; T.out = out;
+    if (shaft_begin(S, p, T))
+        while (shaft_step(S, T)) {}
+    if (steps_out) *steps_out = T.steps;
+    return T.n;
 }
 // The decision of light_visible for one sample from the vertex's list: (W) some listed primitive is hit within EPSILON of dist
 // (already known when `witness`), (O) none is hit closer than that.  Leaf box first, exactly as the walk would.
@@ -805,6 +835,22 @@ PT_HD bool list_visible(const SceneView &S, const uint32_t *list, int n, const R
         if (!box_hit(xyz(a), xyz(b), r, &tmin)) continue;
         double t;
         if (prim_hit(S, f2u(a.w), f2u(b.w), r, &t)) {
+            if (fabs(t - dd) < eps) witness = true;
+            else if (t < dd) return false;
+        }
+    }
+    return witness;
+}
+// The same over records already fetched (a warp loads the list of its vertex once, pt_kernels.cu): rec[5 * j .. 5 * j + 4] =
+// leaf (bmin | prim) (bmax | kind), then the primitive's three float4.
+PT_HD bool list_visible_records(const float4 *rec, int n, const Ray &r, float dist, bool witness) {
+    const double eps = (double)kEps, dd = (double)dist;
+    for (int j = 0; j < n; ++j) {
+        const float4 a = rec[5 * j], b = rec[5 * j + 1];
+        float tmin;
+        if (!box_hit(xyz(a), xyz(b), r, &tmin)) continue;
+        double t;
+        if (prim_hit_record(rec[5 * j + 2], rec[5 * j + 3], rec[5 * j + 4], f2u(b.w), r, &t)) {
             if (fabs(t - dd) < eps) witness = true;
             else if (t < dd) return false;
         }
