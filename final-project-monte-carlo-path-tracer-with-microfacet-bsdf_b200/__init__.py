@@ -29,12 +29,10 @@ c_uint_p = C.POINTER(C.c_uint32)
 c_double_p = C.POINTER(C.c_double)
 
 SMOOTH_CONDUCTOR, ROUGH_CONDUCTOR, SMOOTH_DIELECTRIC, ROUGH_DIELECTRIC = 0, 1, 2, 3
-ABI_VERSION = 2
 FLAG_COUNT_TRAVERSAL = 1
 FLAG_SPLIT_WAVELENGTHS = 2
 FLAG_FRESH_FRAME = 4
 FLAG_INDEPENDENT_WAVELENGTHS = 8
-FLAG_NO_CANDIDATE_LISTS = 16
 FIX_DIRECT_LIGHT_SAMPLE, FIX_MODEL_QUALITY, FIX_ADD_DIAMOND, FIX_OUTPUT_PATH = 1, 2, 4, 8
 NAMED_MATERIALS = ["rough_red_conductor", "rough_white_conductor", "green_mirror", "gold_conductor", "silver_mirror",
                    "smooth_glass", "smooth_glass_gem", "clear_rough_plastic", "rough_plastic"]
@@ -79,8 +77,7 @@ class Stats(C.Structure):
                 ("bundles", C.c_uint64), ("paths", C.c_uint64), ("rays_traced_closest", C.c_uint64),
                 ("rays_traced_shadow", C.c_uint64), ("rays_reference", C.c_uint64), ("nodes_fetched", C.c_uint64),
                 ("prims_tested", C.c_uint64), ("extend_nodes", C.c_uint64), ("extend_prims", C.c_uint64),
-                ("shadow_nodes", C.c_uint64), ("shadow_prims", C.c_uint64), ("vertices_shaded", C.c_uint64), ("max_depth", C.c_uint32), ("waves", C.c_uint32),
-                ("shadow_rays_listed", C.c_uint64)]
+                ("shadow_nodes", C.c_uint64), ("shadow_prims", C.c_uint64), ("vertices_shaded", C.c_uint64), ("max_depth", C.c_uint32), ("waves", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -185,8 +182,6 @@ def gpu_lib():
         if not os.path.exists(GPU_LIB):
             raise RuntimeError(f"{GPU_LIB} is missing: the CUDA extension must be built (there is no CPU fallback)")
         L = C.CDLL(GPU_LIB)
-        if L.b2pt_abi_version() != ABI_VERSION:  # struct layouts below follow include/b2pt.h of that version
-            raise RuntimeError(f"{GPU_LIB} has ABI {L.b2pt_abi_version()}, this binding is for ABI {ABI_VERSION}: rebuild the extension")
         L.b2pt_last_error.restype = C.c_char_p
         L.b2pt_last_error.argtypes = [C.c_void_p]
         L.b2pt_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]

@@ -78,9 +78,8 @@ struct Counters {
     unsigned int n_cur, n_next, n_shadow, n_vis;  // n_shadow: shadow rays queued for traversal; n_vis: visibility slots handed out
     unsigned int n_class[12];
     unsigned int fetch_extend, fetch_shadow;  // dynamic-fetch cursors of the traversal kernels
-    unsigned int n_lit, fetch_shaft;          // accepted light samples of this bounce; cursor of shaft_kernel
+    unsigned int n_lit, pad1;                 // accepted light samples of this bounce
     unsigned long long rays_closest, rays_shadow, rays_reference, nodes, prims, sh_nodes, sh_prims, vertices, bundles;
-    unsigned long long listed;  // light samples decided from their vertex's candidate list (no traversal)
     unsigned int max_depth, pad2;
     // Generation plan of the next bounce, written by plan_generation (one thread) so that the host never has to know the
     // queue length: camera rays [gen_first, gen_first + gen_count) top the queue up to `wave`.
@@ -108,8 +107,6 @@ struct WaveBufs {
     float4 *vtx_pn;  // per shaded vertex: NEE origin p + n * EPSILON | position of its first light-sample draw in the stream
     uint2 *vtx_ps;   // per shaded vertex: pixel, sample (the stream's key)
     uint32_t *vtx_ray;   // per shaded vertex: its ray in the queue
-    uint32_t *vtx_list;  // per shaded vertex: kShaftK candidate leaves (pt::shaft_collect)
-    unsigned char *vtx_lcnt;  // and how many of them are valid (kShaftNone: no list, the samples walk the tree)
     uint32_t *lit_list;  // visibility slots of the accepted light samples
     float *nee_val;      // [visibility slot][3]: the direct-light summand per wavelength
     float4 *sh_o;  // origin.xyz, w = dist
@@ -498,23 +495,19 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
                                                      const uint32_t *__restrict__ vtx_ray, const int *__restrict__ hit_prim,
                                                      const float *__restrict__ hit_t, const unsigned *__restrict__ n_ptr,
                                                      unsigned char *__restrict__ vis, float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt,
-                                                     uint32_t k0, uint32_t k1, const uint32_t *__restrict__ vtx_list, const unsigned char *__restrict__ vtx_lcnt) {
+                                                     uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
     const unsigned ndir = (unsigned)S.n_dir;
-    unsigned listed = 0;
-    __shared__ float4 s_rec[kWarps][5 * kShaftK];  // the list of the warp's current vertex, fetched once: leaf box | prim | kind, primitive record
     for (unsigned it = blockIdx.x * kBlock; it < rounded; it += gridDim.x * kBlock) {
         const unsigned i = it + threadIdx.x;
-        bool queue = false, from_list = false;
+        bool queue = false;
         int w = 0;
-        unsigned v = 0;
         f3 pn = mk3(0, 0, 0);
         NeeGeom g;
         g.ws = mk3(0, 0, 1); g.dist = 0.f;
         if (i < n) {
-            v = i / ndir;
-            const unsigned k = i - v * ndir;
+            const unsigned v = i / ndir, k = i - v * ndir;
             const float4 a = vtx_pn[v];
             const uint2 ps = vtx_ps[v];
             pn = xyz(a);
@@ -543,43 +536,9 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
             }
             if (dead) vis[i] = 0;
             else {
-                const Ray sr = make_ray(pn, g.ws);
-                w = window_witness(S, sr, g.dist, g.lnode);
+                w = window_witness(S, make_ray(pn, g.ws), g.dist, g.lnode);
                 if (w == 0) vis[i] = 0;
-                else {
-                    // a vertex with a candidate list: its samples test exactly the listed primitives (pt::list_visible), all
-                    // lanes of a vertex reading the same records; rays that need the reference's topology walk it as before
-                    const unsigned lc = vtx_lcnt ? vtx_lcnt[v] : kShaftNone;
-                    if (lc != kShaftNone && !ray_needs_reference_tree(sr)) from_list = true;
-                    else queue = true;
-                }
-            }
-        }
-        if (vtx_lcnt) {
-            // The lanes of a vertex (all 32 when n_dir is 32) test the same list: the warp fetches it once, lane j the j-th entry
-            // (leaf, then its primitive: every load of the list in flight together), and each sample reads the records from shared memory.
-            const unsigned lane = threadIdx.x & 31u;
-            float4 *rec = s_rec[threadIdx.x >> 5];
-            unsigned pending = __ballot_sync(0xffffffffu, from_list);
-            while (pending) {
-                const unsigned vv = __shfl_sync(0xffffffffu, v, __ffs(pending) - 1);
-                const unsigned cntv = vtx_lcnt[vv];
-                if (lane < cntv) {
-                    const uint32_t ref = vtx_list[(size_t)vv * kShaftK + lane];
-                    const float4 *qn = S.nodes + 4 * (size_t)(ref >> 1) + 2 * (ref & 1u);
-                    const float4 a = PT_LDG4(qn), b = PT_LDG4(qn + 1);
-                    const float4 *qt = S.tri + 3 * (size_t)f2u(a.w);
-                    rec[5 * lane] = a; rec[5 * lane + 1] = b;
-                    rec[5 * lane + 2] = PT_LDG4(qt); rec[5 * lane + 3] = PT_LDG4(qt + 1); rec[5 * lane + 4] = PT_LDG4(qt + 2);
-                }
-                __syncwarp();
-                const bool mine = from_list && v == vv;
-                if (mine) {
-                    vis[i] = list_visible_records(rec, (int)cntv, make_ray(pn, g.ws), g.dist, w == 1) ? 1 : 0;
-                    ++listed;
-                }
-                __syncwarp();
-                pending &= ~__ballot_sync(0xffffffffu, mine);
+                else queue = true;
             }
         }
         const unsigned qx = block_alloc(queue ? 1u : 0u, &cnt->n_shadow);
@@ -588,49 +547,6 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
             // w == 1: a witness exists, only occluders are searched (phase 2); w < 0: no table entry, search the window first
             sh_d[qx] = make_float4(g.ws.x, g.ws.y, g.ws.z, __uint_as_float(i | (w < 0 ? 0x80000000u : 0u)));
         }
-    }
-    if (vtx_lcnt) {
-        listed = warp_sum(listed);
-        if ((threadIdx.x & 31u) == 0 && listed) atomicAdd(&cnt->listed, (unsigned long long)listed);
-    }
-}
-
-// ---- shaft: the candidate list of every shaded vertex (pt::shaft_step), persistent warps with dynamic fetch like extend -------------
-__global__ void __launch_bounds__(kBlock, 8) shaft_kernel(SceneView S, const float4 *__restrict__ vtx_pn, const unsigned *__restrict__ n_vis_ptr,
-                                                          unsigned *__restrict__ next, uint32_t *__restrict__ vtx_list, unsigned char *__restrict__ vtx_lcnt) {
-    const unsigned nv = *n_vis_ptr / (unsigned)S.n_dir;
-    const unsigned lane = threadIdx.x & 31u;
-    bool has = false, exhausted = false;
-    unsigned v = 0;
-    ShaftTrav T;
-    uint32_t T_stack[kStackSize];
-    T.stk = T_stack;
-    T.out = vtx_list;
-    shaft_begin(S, mk3(0, 0, 0), T);
-    Fetch F = fetch_begin(nv);
-    for (;;) {
-        if (!exhausted) {
-            const unsigned got = fetch_rays(F, !has, nv, next, lane);
-            if (!has && got != 0xFFFFFFFFu) {
-                v = got;
-                T.out = vtx_list + (size_t)v * kShaftK;
-                if (shaft_begin(S, xyz(vtx_pn[v]), T)) has = true;
-                else vtx_lcnt[v] = (unsigned char)kShaftNone;
-            }
-            exhausted = F.dry && F.lo >= F.hi;
-        }
-        unsigned act = __ballot_sync(0xffffffffu, has);
-        if (!act) {
-            if (exhausted) break;
-            continue;
-        }
-        do {
-            if (has && !shaft_step(S, T)) {
-                vtx_lcnt[v] = (unsigned char)(T.n < 0 ? kShaftNone : (unsigned)T.n);
-                has = false;
-            }
-            act = __ballot_sync(0xffffffffu, has);
-        } while (act && (exhausted || __popc(act) > kRefillBelow));
     }
 }
 
@@ -1110,7 +1026,6 @@ __global__ void swap_counts_kernel(Counters *cnt) {
     for (int c = 0; c < kClasses; ++c) cnt->n_class[c] = 0;
     cnt->fetch_extend = 0;
     cnt->fetch_shadow = 0;
-    cnt->fetch_shaft = 0;
     cnt->n_lit = 0;
     plan_generation(cnt);
 }
@@ -1295,7 +1210,6 @@ struct b2pt_ctx {
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[kSide] = {nullptr, nullptr, nullptr};
     int n_side = kSide;  // 0: everything on the main stream (B2PT_SIDE_STREAMS=0)
-    int shaft_min_ndir = 8;  // candidate lists per vertex from this many light samples on (B2PT_SHAFT_MIN_NDIR, experiments)
     std::string err;
     bool has_scene = false;
     SceneView view{};
@@ -1375,7 +1289,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t per_queue = al(rays * 16) * 2 + al(rays * 4) * 2 + al(rays * 16 * 6);
     size_t shadows = rays * (size_t)ndir;
-    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows) + al(rays * 16) + al(rays * 8) + al(rays * 4) + al(shadows * 4) + al(shadows * 12) + al(rays * 4 * kShaftK) + al(rays);
+    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows) + al(rays * 16) + al(rays * 8) + al(rays * 4) + al(shadows * 4) + al(shadows * 12);
     release(ctx->wave_mem);
     ctx->wave_rays = 0;
     int r = ensure(ctx, ctx->wave_mem, total);
@@ -1396,8 +1310,6 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     ctx->wb.vtx_pn = (float4 *)take(rays * 16);
     ctx->wb.vtx_ps = (uint2 *)take(rays * 8);
     ctx->wb.vtx_ray = (uint32_t *)take(rays * 4);
-    ctx->wb.vtx_list = (uint32_t *)take(rays * 4 * kShaftK);
-    ctx->wb.vtx_lcnt = (unsigned char *)take(rays);
     ctx->wb.lit_list = (uint32_t *)take(shadows * 4);
     ctx->wb.nee_val = (float *)take(shadows * 12);
     ctx->wb.sh_o = (float4 *)take(shadows * 16);
@@ -1427,9 +1339,6 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     // 0: the three wavelength paths of a sample share rays while their geometry coincides; 1: three rays from the camera on, same
     // stream (a self-check); 2: three rays AND three streams (the reference's independent draws per castRay call)
     const int split = (p->flags & B2PT_FLAG_INDEPENDENT_WAVELENGTHS) ? 2 : ((p->flags & B2PT_FLAG_SPLIT_WAVELENGTHS) ? 1 : 0);
-    // candidate lists per vertex (shaft_kernel): one tree walk with a cone per vertex instead of n_dir walks with rays — pays from a
-    // handful of samples per vertex on
-    const bool lists = S.shaft_m > 0.f && S.n_dir >= ctx->shaft_min_ndir && !(p->flags & B2PT_FLAG_NO_CANDIDATE_LISTS);
 
     GenParams gp{};
     gp.mode = job.mode;
@@ -1508,13 +1417,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             terminal_kernel<<<grid_for(n, ctx, 16), kBlock, 0, ctx->side[0]>>>(S, qa, ctx->wb.lists, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
         }
         if (S.enable_shadow) {
-            if (lists) {
-                shaft_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, &dc->n_vis, &dc->fetch_shaft, ctx->wb.vtx_list, ctx->wb.vtx_lcnt);
-                launches++;
-            }
             nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, qa, ctx->wb.vtx_pn, ctx->wb.vtx_ps, ctx->wb.vtx_ray, ctx->wb.hit_prim,
-                                                                                ctx->wb.hit_t, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o, ctx->wb.sh_d, dc, gp.k0, gp.k1,
-                                                                                lists ? ctx->wb.vtx_list : nullptr, lists ? ctx->wb.vtx_lcnt : nullptr);
+                                                                                ctx->wb.hit_t, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o, ctx->wb.sh_d, dc, gp.k0, gp.k1);
             launches++;
             CU(cudaEventRecord(ctx->tev[ring][2], st));
             if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
@@ -1603,7 +1507,6 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         stats->nodes_fetched = h.nodes + h.sh_nodes; stats->prims_tested = h.prims + h.sh_prims;
         stats->extend_nodes = h.nodes; stats->extend_prims = h.prims; stats->shadow_nodes = h.sh_nodes; stats->shadow_prims = h.sh_prims;
         stats->vertices_shaded = h.vertices;
-        stats->shadow_rays_listed = h.listed;
         stats->max_depth = h.max_depth; stats->waves = h.waves;
     }
     return B2PT_OK;
@@ -1683,7 +1586,6 @@ int b2pt_create(b2pt_ctx **out, int device) {
     for (auto &ev : c->fork_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     for (auto &ev : c->join_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("B2PT_SIDE_STREAMS")) c->n_side = std::max(0, std::min((int)b2pt_ctx::kSide, atoi(e)));
-    if (const char *e = getenv("B2PT_SHAFT_MIN_NDIR")) c->shaft_min_ndir = std::max(1, atoi(e));
     ok = ok && cudaMalloc((void **)&c->d_cnt, sizeof(Counters)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_ring, 2 * sizeof(Counters)) == cudaSuccess;
@@ -1775,7 +1677,6 @@ int b2pt_upload_scene(b2pt_ctx *ctx, const b2pt_scene_desc *d) {
     v.n_lights = (int)d->n_lights;
     for (int k = 0; k < 3; ++k) v.light_c[k] = packed.light_sphere[k];
     v.light_r = packed.light_sphere[3];
-    v.shaft_m = packed.shaft_m;
     for (int k = 0; k < 3; ++k) { v.light_bmin[k] = packed.light_box[k]; v.light_bmax[k] = packed.light_box[3 + k]; }
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height;
     v.env = nullptr;
@@ -1952,7 +1853,7 @@ int b2pt_group_render(b2pt_ctx **ctxs, int n, const b2pt_camera *cam, const b2pt
             stats->kernel_launches += st[i].kernel_launches; stats->extend_launches += st[i].extend_launches; stats->shadow_launches += st[i].shadow_launches;
             stats->bundles += st[i].bundles; stats->paths += st[i].paths;
             stats->rays_traced_closest += st[i].rays_traced_closest; stats->rays_traced_shadow += st[i].rays_traced_shadow;
-            stats->rays_reference += st[i].rays_reference; stats->vertices_shaded += st[i].vertices_shaded; stats->shadow_rays_listed += st[i].shadow_rays_listed;
+            stats->rays_reference += st[i].rays_reference; stats->vertices_shaded += st[i].vertices_shaded;
             stats->nodes_fetched += st[i].nodes_fetched; stats->prims_tested += st[i].prims_tested;
             stats->max_depth = std::max(stats->max_depth, st[i].max_depth); stats->waves += st[i].waves;
         }

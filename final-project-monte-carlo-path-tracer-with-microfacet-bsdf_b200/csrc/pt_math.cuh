@@ -230,7 +230,6 @@ struct SceneView {
     const int *lt_off, *lt_cnt;
     float light_c[3], light_r;  // a sphere around every point a light sample can fall on (pt_pack.hpp); light_r < 0: unknown
     float light_bmin[3], light_bmax[3];  // and an axis-aligned box around them (valid when light_r >= 0)
-    float shaft_m;             // inflation of the cone-vs-box test of shaft_collect (pt_pack.hpp); <= 0: no candidate lists
     int use_env, env_w, env_h;
     const float4 *env;      // texels as float4 (rgb, 0)
     unsigned long long env_tex;  // the same texels as a point-sampled CUDA texture object (device only; 0 = use `env`)
@@ -351,9 +350,12 @@ PT_HD float prune_bound(double best) {
 }
 
 // primitive test of a leaf: Triangle::getIntersection or Sphere::getIntersection
-// ... from the primitive's interleaved record (S.tri: v0, e1, e2 | centre, radius)
-PT_HD bool prim_hit_record(float4 a, float4 b, float4 c, uint32_t kind, const Ray &r, double *t) {
+PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
+    const float4 *q = S.tri + 3 * (size_t)prim;
+    float4 a = PT_LDG4(q);
+    float4 b = PT_LDG4(q + 1);
     if (kind == NODE_TRIANGLE) {
+        float4 c = PT_LDG4(q + 2);
         double u, v;
         return tri_hit(xyz(a), xyz(b), xyz(c), r, t, &u, &v);
     }
@@ -361,14 +363,6 @@ PT_HD bool prim_hit_record(float4 a, float4 b, float4 c, uint32_t kind, const Ra
     bool ok = sphere_hit(xyz(a), b.x, r, &tf);
     *t = (double)tf;
     return ok;
-}
-PT_HD bool prim_hit(const SceneView &S, uint32_t prim, uint32_t kind, const Ray &r, double *t) {
-    const float4 *q = S.tri + 3 * (size_t)prim;
-    float4 a = PT_LDG4(q);
-    float4 b = PT_LDG4(q + 1);
-    float4 c = b;
-    if (kind == NODE_TRIANGLE) c = PT_LDG4(q + 2);
-    return prim_hit_record(a, b, c, kind, r, t);
 }
 
 // The traversal tree may be any tree over the reference's leaf boxes (pt_build.hpp explains why the hits are the same)
@@ -713,149 +707,6 @@ PT_HD bool light_visible(const SceneView &S, const Ray &r, float dist, TravStats
     shadow_begin(S, r, T, dist, w == 1 ? 2 : 1);
     while (shadow_step<COUNT>(S, r, dist, T, st)) {}
     return T.visible;
-}
-
-// ---- candidate lists: every primitive any light sample of one vertex can ever test ---------------------------------------
-// All n_dir shadow rays of a vertex leave the same point p and end on the lights, i.e. inside the lights' box L.  The reference
-// tests a primitive for such a ray only when the ray passes the primitive's own leaf box (Bounds3::IntersectP), so the
-// primitives that can matter to ANY of those rays are the ones whose leaf box meets the cone { p + s (q - p) : q in L, s >= 0 }.
-// shaft_collect walks the traversal tree once per vertex with a conservative cone-vs-box test and lists those leaves; when the
-// list is short, each sample is decided by testing exactly the listed primitives the reference's way (leaf box first, then the
-// primitive, then the window / occluder classification of light_visible) instead of walking the tree n_dir times.  Same tests
-// on the same primitives, hence the same decision.  Conservative means: L and every box are inflated by S.shaft_m, which
-// exceeds what the float box test can accept beyond the exact box (EPSILON in t + 1.8e-7 per slab product), the
-// normalisation error of the ray direction and the rounding of the sample point, all scaled by the scene's largest coordinate
-// (pt_pack.hpp).  Interior boxes contain their leaves, so pruning with the same test loses no leaf.
-#ifndef B2PT_SHAFT_K
-#define B2PT_SHAFT_K 32
-#endif
-constexpr int kShaftK = B2PT_SHAFT_K;     // longest list kept; a longer one means "walk the tree as before"
-constexpr uint32_t kShaftNone = 0xFFu;    // stored count of a vertex without a list
-#ifndef B2PT_SHAFT_MAX_STEPS
-#define B2PT_SHAFT_MAX_STEPS 192
-#endif
-constexpr int kShaftMaxSteps = B2PT_SHAFT_MAX_STEPS;  // sibling pairs a collection may visit before it gives up
-struct Cone {
-    f3 p, dlo, dhi, rlo, rhi;  // apex, (L.min - p, L.max - p) and their reciprocals
-    float m;
-    bool ok;
-};
-PT_HD Cone cone_make(const SceneView &S, f3 p) {
-    Cone c;
-    c.m = S.shaft_m;
-    c.p = p;
-    c.dlo = mk3(S.light_bmin[0] - c.m - p.x, S.light_bmin[1] - c.m - p.y, S.light_bmin[2] - c.m - p.z);
-    c.dhi = mk3(S.light_bmax[0] + c.m - p.x, S.light_bmax[1] + c.m - p.y, S.light_bmax[2] + c.m - p.z);
-    c.rlo = mk3(1.0f / c.dlo.x, 1.0f / c.dlo.y, 1.0f / c.dlo.z);
-    c.rhi = mk3(1.0f / c.dhi.x, 1.0f / c.dhi.y, 1.0f / c.dhi.z);
-    const float q = (fabsf(p.x) + fabsf(p.y)) + fabsf(p.z);
-    c.ok = S.shaft_m > 0.f && S.light_r >= 0.f && q < INFINITY;
-    return c;
-}
-// One axis: the cone's extent at parameter s is [p + s dlo, p + s dhi]; it overlaps [bmin, bmax] iff s dlo <= bmax - p and
-// s dhi >= bmin - p.  Each inequality bounds s from one side (which one depends on the sign of its slope) or, with a zero slope,
-// holds for every s or for none.
-PT_HD bool cone_axis(float p, float dlo, float dhi, float rlo, float rhi, float bmin, float bmax, float *slo, float *shi) {
-    const float u = bmax - p, l = bmin - p;
-    bool ok = true;
-    if (dlo > 0.f) *shi = fminf(*shi, u * rlo);
-    else if (dlo < 0.f) *slo = fmaxf(*slo, u * rlo);
-    else ok = u >= 0.f;
-    if (dhi > 0.f) *slo = fmaxf(*slo, l * rhi);
-    else if (dhi < 0.f) *shi = fminf(*shi, l * rhi);
-    else ok = ok && l <= 0.f;
-    return ok;
-}
-PT_HD bool cone_meets_box(const Cone &c, f3 bmin, f3 bmax) {
-    float slo = 0.f, shi = INFINITY;
-    bool ok = cone_axis(c.p.x, c.dlo.x, c.dhi.x, c.rlo.x, c.rhi.x, bmin.x - c.m, bmax.x + c.m, &slo, &shi);
-    ok = cone_axis(c.p.y, c.dlo.y, c.dhi.y, c.rlo.y, c.rhi.y, bmin.y - c.m, bmax.y + c.m, &slo, &shi) && ok;
-    ok = cone_axis(c.p.z, c.dlo.z, c.dhi.z, c.rlo.z, c.rhi.z, bmin.z - c.m, bmax.z + c.m, &slo, &shi) && ok;
-    // the inflation leaves an s-interval of width >= 2 m / |q - p| for every box the exact cone touches; the factor covers the
-    // rounding of the six products when s is large (boxes far behind the lights)
-    return ok && !(slo > shi * 1.00001f + 1e-6f);
-}
-// Leaves (as 2 * pair + side of S.nodes) whose box meets the cone of a vertex, one sibling pair per step so that the kernel can
-// refill finished lanes (pt_kernels.cu shaft_kernel).  T.n ends as the number of leaves, or -1 when there are more than kShaftK,
-// the walk is too long, or the scene has no usable light box.  stk: kStackSize entries, out: kShaftK entries.
-struct ShaftTrav {
-    Cone c;
-    uint32_t pair;
-    int n, sp, steps;
-    uint32_t *stk, *out;
-};
-PT_HD bool shaft_begin(const SceneView &S, f3 p, ShaftTrav &T) {
-    T.c = cone_make(S, p);
-    T.pair = 0; T.n = 0; T.sp = 0; T.steps = 0;
-    if (!T.c.ok) { T.n = -1; return false; }
-    return true;
-}
-// Returns false when the collection has finished (T.n).
-PT_HD bool shaft_step(const SceneView &S, ShaftTrav &T) {
-    if (++T.steps > kShaftMaxSteps) { T.n = -1; return false; }
-    const float4 *q = S.nodes + 4 * (size_t)T.pair;
-    const float4 l0 = PT_LDG4(q), l1 = PT_LDG4(q + 1), r0 = PT_LDG4(q + 2), r1 = PT_LDG4(q + 3);
-    const uint32_t lk = f2u(l1.w), rk = f2u(r1.w);
-    // EMPTY fillers carry NaN boxes: every comparison of the cone test is false for them, which would read as "meets"
-    const bool hl = lk != NODE_EMPTY && cone_meets_box(T.c, xyz(l0), xyz(l1));
-    const bool hr = rk != NODE_EMPTY && cone_meets_box(T.c, xyz(r0), xyz(r1));
-    const bool ll = hl && lk != NODE_INTERIOR, rl = hr && rk != NODE_INTERIOR;
-    if (T.n + (ll ? 1 : 0) + (rl ? 1 : 0) > kShaftK) { T.n = -1; return false; }
-    if (ll) T.out[T.n++] = 2u * T.pair;
-    if (rl) T.out[T.n++] = 2u * T.pair + 1u;
-    const bool il = hl && lk == NODE_INTERIOR, ir = hr && rk == NODE_INTERIOR;
-    if (il && ir) {
-        if (T.sp >= kStackSize) { T.n = -1; return false; }
-        T.stk[T.sp++] = f2u(r0.w);
-        T.pair = f2u(l0.w);
-        return true;
-    }
-    if (il) { T.pair = f2u(l0.w); return true; }
-    if (ir) { T.pair = f2u(r0.w); return true; }
-    if (T.sp > 0) { T.pair = T.stk[--T.sp]; return true; }
-    return false;
-}
-PT_HD int shaft_collect(const SceneView &S, f3 p, uint32_t *out, uint32_t *stk, int *steps_out = nullptr) {
-    ShaftTrav T;
-    T.stk = stk; T.out = out;
-    if (shaft_begin(S, p, T))
-        while (shaft_step(S, T)) {}
-    if (steps_out) *steps_out = T.steps;
-    return T.n;
-}
-// The decision of light_visible for one sample from the vertex's list: (W) some listed primitive is hit within EPSILON of dist
-// (already known when `witness`), (O) none is hit closer than that.  Leaf box first, exactly as the walk would.
-PT_HD bool list_visible(const SceneView &S, const uint32_t *list, int n, const Ray &r, float dist, bool witness) {
-    const double eps = (double)kEps, dd = (double)dist;
-    for (int j = 0; j < n; ++j) {
-        const uint32_t ref = list[j];
-        const float4 *q = S.nodes + 4 * (size_t)(ref >> 1) + 2 * (ref & 1u);
-        const float4 a = PT_LDG4(q), b = PT_LDG4(q + 1);
-        float tmin;
-        if (!box_hit(xyz(a), xyz(b), r, &tmin)) continue;
-        double t;
-        if (prim_hit(S, f2u(a.w), f2u(b.w), r, &t)) {
-            if (fabs(t - dd) < eps) witness = true;
-            else if (t < dd) return false;
-        }
-    }
-    return witness;
-}
-// The same over records already fetched (a warp loads the list of its vertex once, pt_kernels.cu): rec[5 * j .. 5 * j + 4] =
-// leaf (bmin | prim) (bmax | kind), then the primitive's three float4.
-PT_HD bool list_visible_records(const float4 *rec, int n, const Ray &r, float dist, bool witness) {
-    const double eps = (double)kEps, dd = (double)dist;
-    for (int j = 0; j < n; ++j) {
-        const float4 a = rec[5 * j], b = rec[5 * j + 1];
-        float tmin;
-        if (!box_hit(xyz(a), xyz(b), r, &tmin)) continue;
-        double t;
-        if (prim_hit_record(rec[5 * j + 2], rec[5 * j + 3], rec[5 * j + 4], f2u(b.w), r, &t)) {
-            if (fabs(t - dd) < eps) witness = true;
-            else if (t < dd) return false;
-        }
-    }
-    return witness;
 }
 
 // ---- the visibility walk over the four-wide tree -------------------------------------------------------------------------

@@ -23,7 +23,6 @@ struct PackedScene {
     int fast_depth = 0;
     float light_sphere[4] = {0.f, 0.f, 0.f, -1.f};  // centre, radius of a sphere around every light primitive (radius < 0: none)
     float light_box[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // and the axis-aligned box around them (min, max)
-    float shaft_m = -1.f;               // inflation used by pt::shaft_collect (<= 0: no candidate lists), see below
     QuadTree quads;                     // nodes_fast collapsed four-wide; empty when its stack need exceeds kStackSize4
     // Per light-tree node (leaves only): the primitives that can be hit within the visibility window of a point sampled
     // on that light triangle — the triangle itself first, then every primitive whose box comes within `delta` of its box.
@@ -241,21 +240,6 @@ inline void pack_scene(const b2pt_scene_desc *d, PackedScene &out, bool build_fa
                 for (int k = 0; k < 3; ++k) { out.light_box[k] = lb.mn[k]; out.light_box[3 + k] = lb.mx[k]; }
             }
         }
-    }
-    // Candidate lists (pt::shaft_collect) need a bound on how far outside a leaf box a ray can pass and still be accepted by the
-    // float box test, plus the direction's normalisation error and the rounding of the sample point.  With E the largest
-    // coordinate magnitude of the scene: EPSILON (1e-4, in t = distance) + 2 slabs x 3 roundings x 2E (7.2e-7 E) + direction
-    // (3 ulp over a path of <= 2 sqrt(3) E: 7e-7 E) + sample point (2e-7 E) < 1e-4 + 1.7e-6 E; the margin is ten times that.
-    out.shaft_m = -1.f;
-    if (out.light_sphere[3] >= 0.f) {
-        float E = 0.f;
-        for (const b2pt_node &n : out.nodes_fast) {
-            if (n.kind == B2PT_NODE_EMPTY) continue;
-            for (int k = 0; k < 3; ++k) E = std::fmax(E, std::fmax(std::fabs(n.bmin[k]), std::fabs(n.bmax[k])));
-        }
-        for (int k = 0; k < 6; ++k) E = std::fmax(E, std::fabs(out.light_box[k]));
-        const float m = 1e-3f + 2e-5f * E;
-        if (std::isfinite(m) && E < 1e6f) out.shaft_m = m;  // beyond 1e6 the float grid is coarser than EPSILON: not worth a proof
     }
     out.mats.resize(d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B2PT_ABI_VERSION 2
+#define B2PT_ABI_VERSION 1
 
 /* status codes (negative = error; text via b2pt_last_error) */
 enum {
@@ -147,8 +147,6 @@ enum {
     B2PT_FLAG_SPLIT_WAVELENGTHS = 2,/* trace the R, G, B paths of a sample as three separate rays from the camera
                                        on (what the reference does, Renderer.cpp:77-79) instead of sharing rays
                                        while their geometry coincides; same result, used as a self-check          */
-    B2PT_FLAG_NO_CANDIDATE_LISTS = 16, /* walk the tree for every light sample even where a vertex has a short list of the only
-                                       primitives its samples can test (same decisions; a self-check and an A/B switch) */
     B2PT_FLAG_INDEPENDENT_WAVELENGTHS = 8 /* three rays AND three sample streams per sample: R, G and B consume independent
                                        draws like the reference's three castRay calls (Renderer.cpp:77-79).  The default
                                        (one stream shared by the three paths) has the same per-channel expectation but
@@ -172,8 +170,6 @@ typedef struct b2pt_stats {
     uint64_t shadow_nodes, shadow_prims;
     uint64_t vertices_shaded;
     uint32_t max_depth, waves;
-    uint64_t shadow_rays_listed;   /* light samples decided from their vertex's candidate list instead of a
-                                      traversal (ABI 2; not part of rays_traced_shadow)                 */
 } b2pt_stats;
 
 typedef struct b2pt_ctx b2pt_ctx;

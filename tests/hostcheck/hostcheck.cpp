@@ -62,7 +62,6 @@ static void *scene_new(const b2pt_scene_desc *d, bool fast, const BuildOptions *
     v.lt_entries = h->packed.lt_entries.data(); v.lt_off = h->packed.lt_off.data(); v.lt_cnt = h->packed.lt_cnt.data();
     for (int k = 0; k < 3; ++k) v.light_c[k] = h->packed.light_sphere[k];
     v.light_r = h->packed.light_sphere[3];
-    v.shaft_m = h->packed.shaft_m;
     for (int k = 0; k < 3; ++k) { v.light_bmin[k] = h->packed.light_box[k]; v.light_bmax[k] = h->packed.light_box[3 + k]; }
     v.use_env = d->use_env_map; v.env_w = (int)d->env_width; v.env_h = (int)d->env_height; v.env = h->packed.env.data();
     for (int j = 0; j < 3; ++j) v.bg[j] = d->background[j];
@@ -250,78 +249,6 @@ void hc_nee_dead(void *h, const float *o, const float *d, const float *u4, long 
             }
         }
         out_alive[i] = alive;
-    }
-}
-// Candidate lists (pt::shaft_collect / list_visible) against the walk they replace.  Per ray of the batch: its first hit is a vertex
-// (skipped when it is a miss or an emitter); `samples` light samples are drawn from u4[i][s][4] and each is decided twice, by
-// light_visible with the sample's light-tree leaf and by the vertex's list.  out_len[i] = list length (-1: no list, -2: no vertex),
-// out_vis[i * samples + s] = the walk's decision, out_dead[i] (optional) = pt::nee_vertex_is_dead (such a vertex draws no samples in the
-// render path); returns the number of samples where the two disagree (0 = exact).
-long hc_shaft_check(void *h, const float *o, const float *d, const float *u4, long n, int samples, int *out_len, int *out_vis, int *out_dead) {
-    const SceneView &S = ((HcScene *)h)->view;
-    long bad = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : bad)
-    for (long i = 0; i < n; ++i) {
-        out_len[i] = -2;
-        for (int s = 0; s < samples; ++s) out_vis[i * samples + s] = -1;
-        TravStats st{0, 0};
-        Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
-        Hit hit = closest_hit4<false>(S, r, &st);
-        if (hit.prim < 0) continue;
-        Surface sf = surface_at(S, r, hit);
-        if (S.mats[sf.mat].emissive) continue;
-        const f3 pn = sf.p + sf.n * kEps;
-        if (out_dead) out_dead[i] = nee_vertex_is_dead(S, S.mats[sf.mat], -r.d, sf.n, pn) ? 1 : 0;
-        uint32_t list[kShaftK], stk[kStackSize];
-        const int len = shaft_collect(S, pn, list, stk);
-        out_len[i] = len;
-        for (int s = 0; s < samples; ++s) {
-            const float *u = u4 + 4 * ((size_t)i * samples + s);
-            NeeGeom g = nee_geometry(S, pn, u[0], u[1], u[2], u[3]);
-            const Ray sr = make_ray(pn, g.ws);
-            const bool walk = light_visible<false>(S, sr, g.dist, &st, g.lnode);
-            out_vis[i * samples + s] = walk ? 1 : 0;
-            if (len < 0 || ray_needs_reference_tree(sr)) continue;
-            const int w = window_witness(S, sr, g.dist, g.lnode);
-            const bool listed = w == 0 ? false : list_visible(S, list, len, sr, g.dist, w == 1);
-            if (listed != walk) ++bad;
-        }
-    }
-    return bad;
-}
-// The render path's decision for given shadow rays (origin p, direction ws towards a light sample at distance dist, drawn from light
-// leaf lnode): from the candidate list of p where one exists (visible = 0 / 1), else -1 (the ray would walk the tree).
-void hc_shadow_listed(void *h, const float *p, const float *ws, const float *dist, const int *lnode, long n, int *visible, int *len) {
-    const SceneView &S = ((HcScene *)h)->view;
-#pragma omp parallel for schedule(dynamic, 256)
-    for (long i = 0; i < n; ++i) {
-        uint32_t list[kShaftK], stk[kStackSize];
-        const int m = shaft_collect(S, V(p + 3 * i), list, stk);
-        len[i] = m;
-        visible[i] = -1;
-        const Ray sr = make_ray(V(p + 3 * i), V(ws + 3 * i));
-        if (m < 0 || ray_needs_reference_tree(sr)) continue;
-        const int w = window_witness(S, sr, dist[i], lnode ? lnode[i] : -1);
-        visible[i] = w == 0 ? 0 : (list_visible(S, list, m, sr, dist[i], w == 1) ? 1 : 0);
-    }
-}
-// statistics of shaft_collect for the live vertices of a ray batch: steps[i] = sibling pairs visited (0: no live vertex), len[i]
-void hc_shaft_steps(void *h, const float *o, const float *d, long n, int *steps, int *len) {
-    const SceneView &S = ((HcScene *)h)->view;
-    for (long i = 0; i < n; ++i) {
-        steps[i] = 0; len[i] = -2;
-        TravStats st{0, 0};
-        Ray r = make_ray(V(o + 3 * i), V(d + 3 * i));
-        Hit hit = closest_hit4<false>(S, r, &st);
-        if (hit.prim < 0) continue;
-        Surface sf = surface_at(S, r, hit);
-        if (S.mats[sf.mat].emissive) continue;
-        const f3 pn = sf.p + sf.n * kEps;
-        if (nee_vertex_is_dead(S, S.mats[sf.mat], -r.d, sf.n, pn)) continue;
-        uint32_t list[kShaftK], stk[kStackSize];
-        int nsteps = 0;
-        len[i] = shaft_collect(S, pn, list, stk, &nsteps);
-        steps[i] = nsteps;
     }
 }
 void hc_pdf(void *h, int mat, const float *wi, const float *wo, const float *N, const int *wl, const int *refl, long n, float *out) {

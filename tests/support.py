@@ -154,28 +154,6 @@ class HostCheck:
         self.L.hc_nee_dead(self.h, fp(o), fp(d), fp(u4), C.c_long(n), samples, ip(v), ip(a))
         return v, a
 
-    def shaft_check(self, o, d, samples, rng):
-        """Candidate lists (pt::shaft_collect, list_visible) against the walk, for the first hit of every ray and `samples` random
-        light samples each: (number of disagreeing decisions, list length per vertex [-1 no list, -2 no vertex], the walk's decisions,
-        pt::nee_vertex_is_dead per vertex — those draw no samples in the render path)."""
-        o, d = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
-        n = len(o)
-        u4 = ((np.floor(rng.rand(n, samples, 4) * 4294967296.0) + 0.0) / 4294967296.0).astype(np.float32)
-        u4 = np.minimum(u4, np.float32(0.99999994))
-        ln, vis, dead = np.zeros(n, np.int32), np.zeros(n * samples, np.int32), np.zeros(n, np.int32)
-        self.L.hc_shaft_check.restype = C.c_long
-        bad = self.L.hc_shaft_check(self.h, fp(o), fp(d), fp(u4), C.c_long(n), samples, ip(ln), ip(vis), ip(dead))
-        return int(bad), ln, vis.reshape(n, samples), dead
-
-    def shadow_listed(self, p, ws, dist, lnode=None):
-        """Visibility decisions from the candidate list of each ray's origin (pt::shaft_collect + list_visible): (decision 0 / 1, or -1
-        where the origin has no list; list length or -1)."""
-        p, ws, dist = f32(p).reshape(-1, 3), f32(ws).reshape(-1, 3), f32(dist)
-        vis, ln = np.zeros(len(p), np.int32), np.zeros(len(p), np.int32)
-        ln_arg = ip(i32(lnode)) if lnode is not None else None
-        self.L.hc_shadow_listed(self.h, fp(p), fp(ws), fp(dist), ln_arg, C.c_long(len(p)), ip(vis), ip(ln))
-        return vis, ln
-
     def bsdf_eval_returns_zero(self, mat, wi, wo, n, wl, rf):
         """pt::mat_eval_returns_zero: the predicate the nee kernel uses to drop light samples whose summand is zero."""
         wi, wo, n, wl, rf = f32(wi), f32(wo), f32(n), i32(wl), i32(rf)

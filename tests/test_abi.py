@@ -21,7 +21,7 @@ def test_gpu_library_exports():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     lib.b2pt_abi_version.restype = ctypes.c_int
-    assert lib.b2pt_abi_version() == 2
+    assert lib.b2pt_abi_version() == 1
 
 
 def test_host_library_exports():

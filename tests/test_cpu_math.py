@@ -218,28 +218,6 @@ def test_eval_shared_by_the_wavelengths_is_bit_identical():
     hc.close(); sc.close()
 
 
-def test_candidate_lists_decide_like_the_reference(world):
-    """pt::shaft_collect lists every primitive whose leaf box any shadow ray from a vertex to the lights can pass; list_visible tests
-    exactly those.  (i) Against the REFERENCE's closest hit (Scene::intersect + the EPSILON window of Scene.cpp:72-75) on shadow rays
-    the path tracer meets; (ii) against the walk on many more vertices (seen from outside and from inside) x 8 samples each."""
-    name, sc, ref, hc = world
-    _, _, (p, ws, dist, u4) = scenes.ray_batch(ref, sc, n_pixels=4000, samples=2, seed=14)
-    prim_r, t_r, *_ = ref.intersect(p, ws)
-    want = ((prim_r >= 0) & (np.abs(t_r - dist.astype(np.float64)) < np.float64(np.float32(1e-4)))).astype(np.int32)
-    for lnode in (None, hc.sample_light_node(u4)):  # window searched through the list / answered by the light neighbourhood table
-        got, ln = hc.shadow_listed(p, ws, dist, lnode)
-        listed = got >= 0
-        assert listed.mean() > 0.3, (name, listed.mean())
-        assert np.array_equal(got[listed], want[listed]), f"{name}: {(got[listed] != want[listed]).sum()} of {listed.sum()} listed decisions differ"
-        assert 0.01 < want[listed].mean() < 0.99
-        assert ((ln[listed] >= 0) & (ln[listed] <= 32)).all()
-    rng = np.random.RandomState(5)
-    o, d, _ = scenes.ray_batch(ref, sc, n_pixels=3000, samples=1, seed=15)
-    bad, ln, vis, dead = hc.shaft_check(o, d, 8, rng)
-    assert bad == 0, f"{name}: {bad} list decisions differ from the walk"
-    assert (ln >= 0).sum() > 1000
-
-
 def test_vertex_level_verdict_never_drops_a_live_light_sample(world):
     """pt::nee_vertex_is_dead (light_kernel gives such vertices no light samples at all) is conservative: wherever it holds,
     every one of 64 random light samples has a summand that the per-sample predicate also knows to be zero."""

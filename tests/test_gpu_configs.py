@@ -116,30 +116,3 @@ def test_cornell_1024_subset_replay(ctx):
         assert want.mean() > 0.05
         ref.close()
         sc.close()
-
-
-@pytest.mark.parametrize("which", ["chess_nee32", "cornell_nee8", "chess_gem_high_nee32"])
-def test_candidate_lists_leave_every_sample_unchanged(ctx, which):
-    """shaft_kernel + pt::list_visible decide the light samples of a vertex from the short list of the only primitives those shadow
-    rays can test, instead of one tree walk per sample: per-sample radiances are bit-identical with B2PT_FLAG_NO_CANDIDATE_LISTS
-    (every sample walks the tree), most samples are decided from lists and the shadow kernel traverses correspondingly fewer rays."""
-    if which == "chess_nee32":
-        sc, env = scenes.chess(160, 90, dof=True, sky=True, n_dir=32)
-    elif which == "cornell_nee8":
-        sc, env = scenes.cornell(96, 96, n_dir=8)
-    else:
-        sc, env = scenes.chess(160, 90, dof=False, sky=False, n_dir=32, quality="high", fix=b2pt.FIX_MODEL_QUALITY, king="smooth_glass_gem",
-                               left="smooth_glass_gem", right="smooth_glass_gem")
-    ctx.upload(sc)
-    cam = sc.camera
-    px = np.arange(cam.width * cam.height, dtype=np.int32)
-    with_lists, st1 = ctx.render_samples(cam, px, 0, 8)
-    without, st0 = ctx.render_samples(cam, px, 0, 8, flags=b2pt.FLAG_NO_CANDIDATE_LISTS)
-    assert np.array_equal(with_lists.view(np.uint32), without.view(np.uint32))
-    assert st0.shadow_rays_listed == 0
-    assert st1.shadow_rays_listed > 0
-    assert st1.shadow_rays_listed + st1.rays_traced_shadow == st0.rays_traced_shadow  # every surviving sample is decided exactly once
-    assert st1.rays_reference == st0.rays_reference
-    if which != "chess_gem_high_nee32":
-        assert st1.shadow_rays_listed > 0.4 * st0.rays_traced_shadow, (st1.shadow_rays_listed, st0.rays_traced_shadow)
-    sc.close()
