@@ -1357,7 +1357,12 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
     // whatever the queue holds, so the queue is made as long as the memory allows: 48 Mi rays = 82 GB of wave state at four
     // light samples per vertex (measured: 8 Mi 15.0, 16 Mi 15.9, 32 Mi 16.4, 48 Mi 16.6 Grays/s).  Halved until it fits when
     // the device has less to give.
-    size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : (S.n_dir <= 8 ? (size_t)48 << 20 : (size_t)12 << 20);
+    // With more light samples the visibility slots dominate the wave state (3 x (360 + 49 n_dir) bytes per queue entry, worst case
+    // = every ray a shaded vertex): the default keeps the allocation near 120 GB — 20.7 Mi rays at 32 samples (measured on the
+    // 2048-spp frame: 6 Mi 1968 ms, 12 Mi 1829 ms, 16 Mi 1795 ms, 20 Mi 1769 ms; profiles/r02o_queue_sweep_nee32.txt).
+    size_t wave_default = (size_t)48 << 20;
+    if (S.n_dir > 8) wave_default = std::min(wave_default, std::max((size_t)2 << 20, (size_t)(120e9 / (3.0 * (360.0 + 49.0 * S.n_dir)))));
+    size_t wave = p->max_wave_bundles > 0 ? (size_t)p->max_wave_bundles : wave_default;
     if (wave > total) wave = (size_t)std::max<unsigned long long>(total, 1);
     // short jobs: a queue of a sixth of the job (but at least 2 Mi rays) keeps the bounce count low enough and spares the
     // allocation of tens of gigabytes of wave state for a render that lasts a few milliseconds (profiles/r02g_phases_*)
