@@ -107,6 +107,8 @@ struct WaveBufs {
     float4 *vtx_pn;  // per shaded vertex: NEE origin p + n * EPSILON | position of its first light-sample draw in the stream
     uint2 *vtx_ps;   // per shaded vertex: pixel, sample (the stream's key)
     uint32_t *vtx_ray;   // per shaded vertex: its ray in the queue
+    float4 *vtx_geo;     // per shaded vertex, 2 float4: (surface normal | material, wavelength mask << 16, seen-from-inside << 19) (wo, 0) —
+                         // what each of its light samples needs, so nee_kernel does not redo hit_point per sample
     uint32_t *lit_list;  // visibility slots of the accepted light samples
     float *nee_val;      // [visibility slot][3]: the direct-light summand per wavelength
     float4 *sh_o;  // origin.xyz, w = dist
@@ -398,8 +400,8 @@ __device__ __forceinline__ void hit_point(const SceneView &S, const Ray &r, int 
 // the surface it hit — so that the shading kernels run with warps whose lanes take the same code path.
 __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, const unsigned *__restrict__ n_ptr, const int *__restrict__ hit_prim,
                                                        const float *__restrict__ hit_t, uint32_t *__restrict__ sh_base, float4 *__restrict__ vtx_pn,
-                                                       uint2 *__restrict__ vtx_ps, uint32_t *__restrict__ vtx_ray, uint32_t *__restrict__ lists, Counters *cnt, uint32_t k0,
-                                                       uint32_t k1) {
+                                                       uint2 *__restrict__ vtx_ps, uint32_t *__restrict__ vtx_ray, float4 *__restrict__ vtx_geo, uint32_t *__restrict__ lists, Counters *cnt,
+                                                       uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + kBlock - 1) / kBlock * kBlock;
@@ -478,6 +480,10 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
             vtx_pn[v] = make_float4(pn.x, pn.y, pn.z, __uint_as_float((dim & INFO_DIM_MASK) | (path_tag(info) << 20)));  // stream position | stream tag
             vtx_ps[v] = make_uint2(__float_as_uint(o4.w), __float_as_uint(d4.w));
             vtx_ray[v] = i;
+            const f3 wo = -r.d;
+            const uint32_t inner = dot(wo, nn) < 0 ? 1u : 0u;
+            vtx_geo[2 * (size_t)v] = make_float4(nn.x, nn.y, nn.z, __uint_as_float(mat | (((info >> INFO_MASK_SHIFT) & 7u) << 16) | (inner << 19)));
+            vtx_geo[2 * (size_t)v + 1] = make_float4(wo.x, wo.y, wo.z, 0.f);
         }
         // rays the reference needs: ndir shadow rays per shaded vertex and wavelength path, traced here or not
         if (shaded) refs += (unsigned long long)ndir * (unsigned)__popc((info >> INFO_MASK_SHIFT) & 7u);
@@ -491,9 +497,8 @@ __global__ void __launch_bounds__(kBlock) light_kernel(SceneView S, Queue q, con
 // EPSILON of dist" half of the visibility test from the light neighbourhood table (no traversal).  A sample whose window
 // holds no hit is rejected here and never becomes a shadow ray; the others are compacted into the shadow queue for the
 // occluder search.
-__global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const float4 *__restrict__ vtx_pn, const uint2 *__restrict__ vtx_ps,
-                                                     const uint32_t *__restrict__ vtx_ray, const int *__restrict__ hit_prim,
-                                                     const float *__restrict__ hit_t, const unsigned *__restrict__ n_ptr,
+__global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, const float4 *__restrict__ vtx_pn, const uint2 *__restrict__ vtx_ps,
+                                                     const float4 *__restrict__ vtx_geo, const unsigned *__restrict__ n_ptr,
                                                      unsigned char *__restrict__ vis, float4 *__restrict__ sh_o, float4 *__restrict__ sh_d, Counters *cnt,
                                                      uint32_t k0, uint32_t k1) {
     const unsigned n = *n_ptr;
@@ -521,18 +526,9 @@ __global__ void __launch_bounds__(kBlock) nee_kernel(SceneView S, Queue q, const
             // rays; they are still counted as rays it needs (light_kernel), just never traced here.
             bool dead;
             {
-                const unsigned ri = vtx_ray[v];
-                const float4 o4 = q.o[ri], d4 = q.d[ri];
-                const uint32_t mask = (q.info[ri] >> INFO_MASK_SHIFT) & 7u;
-                Ray r;
-                r.o = xyz(o4); r.d = xyz(d4);
-                f3 hp, hn;
-                uint32_t mat, kind;
-                hit_point(S, r, hit_prim[ri], hit_t[ri], &hp, &hn, &mat, &kind);
-                const Material &m = S.mats[mat];
-                const f3 wo = -r.d;
-                const bool inner = dot(wo, hn) < 0;
-                dead = nee_sample_is_dead(m, g, wo, hn, mask, !inner);
+                const float4 ga = vtx_geo[2 * (size_t)v], gb = vtx_geo[2 * (size_t)v + 1];  // written by light_kernel from hit_point
+                const uint32_t bits = __float_as_uint(ga.w);
+                dead = nee_sample_is_dead(S.mats[bits & 0xFFFFu], g, xyz(gb), xyz(ga), (bits >> 16) & 7u, !((bits >> 19) & 1u));
             }
             if (dead) vis[i] = 0;
             else {
@@ -1289,7 +1285,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t per_queue = al(rays * 16) * 2 + al(rays * 4) * 2 + al(rays * 16 * 6);
     size_t shadows = rays * (size_t)ndir;
-    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows) + al(rays * 16) + al(rays * 8) + al(rays * 4) + al(shadows * 4) + al(shadows * 12);
+    size_t total = 2 * per_queue + al(rays * 4) * 3 + al(rays * 4 * kClasses) + al(shadows * 16) * 2 + al(shadows) + al(rays * 16) + al(rays * 8) + al(rays * 4) + al(shadows * 4) + al(shadows * 12) + al(rays * 32);
     release(ctx->wave_mem);
     ctx->wave_rays = 0;
     int r = ensure(ctx, ctx->wave_mem, total);
@@ -1310,6 +1306,7 @@ int setup_wave(b2pt_ctx *ctx, size_t rays, int ndir) {
     ctx->wb.vtx_pn = (float4 *)take(rays * 16);
     ctx->wb.vtx_ps = (uint2 *)take(rays * 8);
     ctx->wb.vtx_ray = (uint32_t *)take(rays * 4);
+    ctx->wb.vtx_geo = (float4 *)take(rays * 32);
     ctx->wb.lit_list = (uint32_t *)take(shadows * 4);
     ctx->wb.nee_val = (float *)take(shadows * 12);
     ctx->wb.sh_o = (float4 *)take(shadows * 16);
@@ -1414,7 +1411,7 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
         CU(cudaEventRecord(ctx->tev[ring][1], st));
         launches++; ext_launches++;
         light_kernel<<<grid_for(n, ctx, 16), kBlock, 0, st>>>(S, qa, &dc->n_cur, ctx->wb.hit_prim, ctx->wb.hit_t, ctx->wb.sh_base, ctx->wb.vtx_pn, ctx->wb.vtx_ps,
-                                                           ctx->wb.vtx_ray, ctx->wb.lists, dc, gp.k0, gp.k1);
+                                                           ctx->wb.vtx_ray, ctx->wb.vtx_geo, ctx->wb.lists, dc, gp.k0, gp.k1);
         launches++;
         if (ctx->n_side > 0) {  // misses, emitters and probe misses need nothing from the light samples: alongside nee / shadow
             CU(cudaEventRecord(ctx->fork_ev[1], st));
@@ -1422,8 +1419,8 @@ int run_render(b2pt_ctx *ctx, const b2pt_camera *cam, const b2pt_render_params *
             terminal_kernel<<<grid_for(n, ctx, 16), kBlock, 0, ctx->side[0]>>>(S, qa, ctx->wb.lists, &dc->n_class[0], ctx->wb.hit_prim, ctx->wb.hit_t, sp);
         }
         if (S.enable_shadow) {
-            nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, qa, ctx->wb.vtx_pn, ctx->wb.vtx_ps, ctx->wb.vtx_ray, ctx->wb.hit_prim,
-                                                                                ctx->wb.hit_t, &dc->n_vis, ctx->wb.vis, ctx->wb.sh_o, ctx->wb.sh_d, dc, gp.k0, gp.k1);
+            nee_kernel<<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.vtx_pn, ctx->wb.vtx_ps, ctx->wb.vtx_geo, &dc->n_vis, ctx->wb.vis,
+                                                                                ctx->wb.sh_o, ctx->wb.sh_d, dc, gp.k0, gp.k1);
             launches++;
             CU(cudaEventRecord(ctx->tev[ring][2], st));
             if (count) shadow_kernel<true><<<grid_for(n * (size_t)S.n_dir, ctx, 16), kBlock, 0, st>>>(S, ctx->wb.sh_o, ctx->wb.sh_d, &dc->n_shadow, &dc->fetch_shadow, ctx->wb.vis, dc);
