@@ -231,9 +231,14 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(Camera cam, GenParams 
 // ---- extend: Scene::intersect for every queued ray ---------------------------------------------------------
 // Persistent warps with dynamic ray fetch: the walks of a warp's 32 rays are stepped together; when the
 // number of lanes still walking falls to kRefillBelow the idle lanes take new rays from the queue (one
-// warp-aggregated atomic), so a few long walks do not leave the warp mostly empty.
+// warp-aggregated atomic).  Round 1 (binary walk) found 12 best; with the four-wide walk and the culled shadow queue the
+// best threshold is 0 — a warp finishes its 32 CONSECUTIVE rays and then takes the next 32: fresh rays (at the root) no
+// longer share the warp with rays deep in the tree, and consecutive queue entries are neighbouring pixels / the light
+// samples of one vertex.  2048-spp-equivalent frame, 32 light samples: 12 -> 439 ms, 8 -> 433, 6 -> 432, 4 -> 432, 2 -> 435,
+// 0 -> 419.5 (profiles/r02r_ab_refill_threshold.txt); what remains of the persistence is the dynamic distribution of the
+// 64-ray chunks over the warps.
 #ifndef B2PT_REFILL_BELOW
-#define B2PT_REFILL_BELOW 12  // measured: flat between 6 and 20, worse above
+#define B2PT_REFILL_BELOW 0
 #endif
 constexpr int kRefillBelow = B2PT_REFILL_BELOW;
 
